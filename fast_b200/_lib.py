@@ -1,0 +1,196 @@
+"""ctypes binding of libfastb.so (C ABI: include/fastb.h).
+
+PyTorch is used only to own device memory and streams; every wrapper takes torch CUDA tensors,
+passes their raw device pointers and the current stream, and raises `FastbError` on a non-zero
+return code.  There is no CPU fallback: importing this module fails loudly when the shared
+library has not been built (python -m fast_b200.build)."""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libfastb.so')
+
+MAX_LAYERS = 32
+AO_NOAO, AO_AO, AO_LGSAO = 0, 1, 2
+ALGO_AUTO, ALGO_DIRECT, ALGO_RADIX = 0, 1, 2
+
+
+class FastbError(RuntimeError):
+    pass
+
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f'{LIB_PATH} not found: the CUDA extension is required (no CPU fallback). '
+        'Build it with `python -m fast_b200.build` (needs nvcc, targets sm_100a).')
+
+lib = C.CDLL(LIB_PATH)
+
+
+class PsdParams(C.Structure):
+    _fields_ = [('n', C.c_int32), ('n_layers', C.c_int32), ('ao_mode', C.c_int32),
+                ('alias', C.c_int32), ('lmax', C.c_int32), ('kmax', C.c_int32),
+                ('reserved0', C.c_int32), ('reserved1', C.c_int32),
+                ('df', C.c_double), ('k', C.c_double), ('wvl', C.c_double),
+                ('L0', C.c_double), ('l0', C.c_double), ('dsubap', C.c_double),
+                ('tloop', C.c_double), ('texp', C.c_double), ('noise_var', C.c_double),
+                ('dtheta', C.c_double * 2),
+                ('h', C.c_double * MAX_LAYERS), ('cn2', C.c_double * MAX_LAYERS),
+                ('vx', C.c_double * MAX_LAYERS), ('vy', C.c_double * MAX_LAYERS)]
+
+
+class PsdInputs(C.Structure):
+    _fields_ = [('d_lf_mask', C.c_void_p), ('d_zfilter', C.c_void_p), ('d_pupil_filter', C.c_void_p)]
+
+
+class PsdOutputs(C.Structure):
+    _fields_ = [('d_powerspec', C.c_void_p), ('d_powerspec_per_layer', C.c_void_p),
+                ('d_turb', C.c_void_p), ('d_g_ao', C.c_void_p), ('d_alias', C.c_void_p),
+                ('d_noise', C.c_void_p), ('d_logamp', C.c_void_p), ('d_integrands', C.c_void_p),
+                ('d_weight', C.c_void_p), ('d_weight_per_layer', C.c_void_p)]
+
+
+class RunParams(C.Structure):
+    _fields_ = [('n', C.c_int32), ('n_pup', C.c_int32), ('lo', C.c_int32), ('coherent', C.c_int32),
+                ('algo', C.c_int32), ('reserved', C.c_int32),
+                ('n_pairs', C.c_int64), ('first_pair', C.c_int64), ('pairs_per_chunk', C.c_int64),
+                ('seed', C.c_uint64), ('u_sum', C.c_double), ('sigma_chi', C.c_float),
+                ('reserved_f', C.c_float)]
+
+
+# every symbol include/fastb.h declares (tests/test_abi.py checks the list against the header)
+_SIGS = {
+    'fastb_psd_build': (C.c_int, [C.POINTER(PsdParams), C.POINTER(PsdInputs), C.POINTER(PsdOutputs), C.c_void_p]),
+    'fastb_make_weight': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_void_p, C.c_void_p]),
+    'fastb_simpson2d': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'fastb_pupil_filter': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    'fastb_pupil_filter_workspace_bytes': (C.c_int64, [C.c_int32]),
+    'fastb_screen_detect_workspace_bytes': (C.c_int64, [C.POINTER(RunParams)]),
+    'fastb_screen_detect': (C.c_int, [C.POINTER(RunParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    'fastb_rng_dump': (C.c_int, [C.c_uint64, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_int64,
+                                 C.c_void_p, C.c_void_p]),
+    'fastb_stats': (C.c_int, [C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_int32, C.c_void_p,
+                              C.c_void_p, C.c_void_p, C.c_void_p]),
+    'fastb_version': (C.c_int, []),
+    'fastb_last_error': (C.c_char_p, []),
+    'fastb_device_count': (C.c_int, []),
+    'fastb_launch_count': (C.c_int64, []),
+    'fastb_reset_launch_count': (None, []),
+}
+for _name, (_res, _args) in _SIGS.items():
+    _fn = getattr(lib, _name)
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+EXPORTED = tuple(_SIGS)
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise FastbError(f'{what} failed (code {rc}): {lib.fastb_last_error().decode()}')
+
+
+def _ptr(t, dtype=None):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise FastbError('expected a CUDA tensor (there is no CPU path)')
+    if not t.is_contiguous():
+        raise FastbError('expected a contiguous tensor')
+    if dtype is not None and t.dtype != dtype:
+        raise FastbError(f'expected dtype {dtype}, got {t.dtype}')
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda():
+    """The product path needs a GPU; fail loudly otherwise."""
+    if not torch.cuda.is_available() or lib.fastb_device_count() < 1:
+        raise FastbError('fast_b200 needs a CUDA device (B200 / sm_100a); no CPU fallback exists')
+
+
+def version():
+    return lib.fastb_version()
+
+
+def launch_count():
+    return int(lib.fastb_launch_count())
+
+
+def reset_launch_count():
+    lib.fastb_reset_launch_count()
+
+
+def psd_build(params: PsdParams, outputs: dict, lf_mask=None, zfilter=None, pupil_filter=None):
+    """outputs: name (field of PsdOutputs without the d_ prefix) -> tensor."""
+    f64 = torch.float64
+    ins = PsdInputs(_ptr(lf_mask, f64), _ptr(zfilter, f64), _ptr(pupil_filter, f64))
+    outs = PsdOutputs()
+    for name, t in outputs.items():
+        want = torch.float32 if name.startswith('weight') else f64
+        setattr(outs, 'd_' + name, _ptr(t, want))
+    _check(lib.fastb_psd_build(C.byref(params), C.byref(ins), C.byref(outs), _stream()), 'fastb_psd_build')
+
+
+def make_weight(W, df, out=None):
+    n = W.shape[-1]
+    batch = W.numel() // (n * n)
+    if out is None:
+        out = torch.empty(W.shape, dtype=torch.float32, device=W.device)
+    _check(lib.fastb_make_weight(_ptr(W, torch.float64), n, batch, float(df), _ptr(out, torch.float32),
+                                 _stream()), 'fastb_make_weight')
+    return out
+
+
+def simpson2d(P, w):
+    n = P.shape[-1]
+    batch = P.numel() // (n * n)
+    out = torch.empty(batch, dtype=torch.float64, device=P.device)
+    _check(lib.fastb_simpson2d(_ptr(P, torch.float64), n, batch, _ptr(w, torch.float64), _ptr(out),
+                               _stream()), 'fastb_simpson2d')
+    return out
+
+
+def pupil_filter(pm):
+    n = pm.shape[-1]
+    out = torch.empty_like(pm)
+    nbytes = lib.fastb_pupil_filter_workspace_bytes(n)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=pm.device)
+    _check(lib.fastb_pupil_filter(_ptr(pm, torch.float64), n, _ptr(out), _ptr(ws), nbytes, _stream()),
+           'fastb_pupil_filter')
+    return out
+
+
+def screen_detect_workspace_bytes(rp: RunParams):
+    nbytes = lib.fastb_screen_detect_workspace_bytes(C.byref(rp))
+    if nbytes < 0:
+        raise FastbError('fastb_screen_detect_workspace_bytes: ' + lib.fastb_last_error().decode())
+    return int(nbytes)
+
+
+def screen_detect(rp: RunParams, weight, U, out_a, out_b, workspace, chi=None, noise=None):
+    f32 = torch.float32
+    _check(lib.fastb_screen_detect(C.byref(rp), _ptr(weight, f32), _ptr(U, f32), _ptr(chi, f32),
+                                   _ptr(noise), _ptr(out_a, f32), _ptr(out_b, f32), _ptr(workspace),
+                                   workspace.numel() * workspace.element_size(), _stream()),
+           'fastb_screen_detect')
+
+
+def rng_dump(seed, pair, n, device, chi_first=0, chi_count=0, want_tile=True):
+    tile = torch.empty((n, n, 2), dtype=torch.float32, device=device) if want_tile else None
+    chi = torch.empty(chi_count, dtype=torch.float32, device=device) if chi_count else None
+    _check(lib.fastb_rng_dump(int(seed), int(pair), n, _ptr(tile), int(chi_first), int(chi_count),
+                              _ptr(chi), _stream()), 'fastb_rng_dump')
+    return tile, chi
+
+
+def stats(r, db_lo, db_hi, nbins, sums, minmax, hist):
+    _check(lib.fastb_stats(_ptr(r, torch.float32), r.numel(), float(db_lo), float(db_hi), int(nbins),
+                           _ptr(sums, torch.float64), _ptr(minmax, torch.float64), _ptr(hist, torch.int64),
+                           _stream()), 'fastb_stats')

@@ -1,0 +1,81 @@
+// Shared helpers of libfastb (sm_100a): error plumbing, launch counting, Philox4x32-10 and
+// Box-Muller.  See include/fastb.h for the contracts.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/fastb.h"
+
+namespace fastb {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+int check_launch(const char* what);          // cudaGetLastError -> FASTB_* (+ counts the launch)
+int fail_cuda(cudaError_t e, const char* what);
+
+#define FASTB_REQUIRE(cond, ...)                                  \
+    do {                                                          \
+        if (!(cond)) {                                            \
+            ::fastb::set_error(__VA_ARGS__);                      \
+            return FASTB_ERR_ARG;                                 \
+        }                                                         \
+    } while (0)
+
+#define FASTB_CUDA(call)                                          \
+    do {                                                          \
+        cudaError_t e__ = (call);                                 \
+        if (e__ != cudaSuccess) return ::fastb::fail_cuda(e__, #call); \
+    } while (0)
+
+constexpr uint32_t kPhiloxM0 = 0xD2511F53u;
+constexpr uint32_t kPhiloxM1 = 0xCD9E8D57u;
+constexpr uint32_t kPhiloxW0 = 0x9E3779B9u;
+constexpr uint32_t kPhiloxW1 = 0xBB67AE85u;
+constexpr uint32_t kStreamNoise = 0x5CE7E000u;
+constexpr uint32_t kStreamChi = 0x10CA3900u;
+
+// Philox4x32-10 (Salmon et al. SC'11).  Key schedule is uniform across the warp.
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                               uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const uint32_t hi0 = __umulhi(kPhiloxM0, c0), lo0 = kPhiloxM0 * c0;
+        const uint32_t hi1 = __umulhi(kPhiloxM1, c2), lo1 = kPhiloxM1 * c2;
+        c0 = hi1 ^ c1 ^ k0;
+        c1 = lo1;
+        c2 = hi0 ^ c3 ^ k1;
+        c3 = lo0;
+        k0 += kPhiloxW0;
+        k1 += kPhiloxW1;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
+// top 23 bits -> [0, 1) exactly, without an int->float conversion
+__device__ __forceinline__ float u23(uint32_t w) {
+    return __uint_as_float(0x3f800000u | (w >> 9)) - 1.0f;
+}
+
+// Box-Muller: radius from wa (argument in (0, 1]), angle from wb.  MUFU lg2 / sqrt / sin / cos.
+__device__ __forceinline__ float2 box_muller(uint32_t wa, uint32_t wb) {
+    const float u1 = 2.0f - __uint_as_float(0x3f800000u | (wa >> 9));     // 1 - (wa>>9) 2^-23
+    const float rad = sqrtf(-1.3862943611198906f * __log2f(u1));          // sqrt(-2 ln u1)
+    const float ang = 6.283185307179586f * u23(wb);
+    float s, c;
+    __sincosf(ang, &s, &c);
+    return make_float2(rad * c, rad * s);
+}
+
+// standard normal n_i used for the log-amplitude of global realisation index i
+__device__ __forceinline__ float chi_normal(uint64_t seed, uint64_t i) {
+    const uint64_t call = i >> 2;
+    const uint4 w = philox4x32_10((uint32_t)call, (uint32_t)(call >> 32), 0u, kStreamChi,
+                                  (uint32_t)seed, (uint32_t)(seed >> 32));
+    const int sel = (int)(i & 3);
+    const float2 n = (sel < 2) ? box_muller(w.x, w.y) : box_muller(w.z, w.w);
+    return (sel & 1) ? n.y : n.x;
+}
+
+}  // namespace fastb

@@ -1,0 +1,184 @@
+// Register-resident line FFT for N = 2^LOG2N (64..2048), 16 complex elements per thread,
+// N/16 threads per line.  Inverse sign convention: X[k] = sum_n x[n] exp(+2 pi i n k / N).
+//
+// Decomposition (decimation in frequency), S1 = N/16 threads per line:
+//   phase A  thread t holds x[t + S1 m], m = 0..15: 16-point DFT over m -> a = k mod 16,
+//            twiddle by w_N^(t a), exchange through the line buffer.
+//   N >= 256 (S1 = 16 S2): thread u = a S2 + t2 gathers t = t2 + S2 m2 and does a second
+//   phase B  16-point DFT over m2 -> a2, twiddle by w_S1^(t2 a2).  S2 == 1: done,
+//            k = a + 16 a2.  Otherwise a last exchange and
+//   phase C  16/S2 DFTs of length S2 over t2 -> b2,  k = a + 16 (a2 + 16 b2).
+//   N = 64, 128 (S1 = 4, 8): phase C directly after phase A with length S1 over t,
+//            k = a + 16 b.
+// The functions are __host__ __device__ so that tests/host_fft_emul.cu can run the exact
+// index algebra on the CPU (threads emulated sequentially between the sync points).
+#pragma once
+#include <cuda_runtime.h>
+
+#ifndef FASTB_HD
+#define FASTB_HD __host__ __device__ __forceinline__
+#endif
+
+namespace fastb {
+
+FASTB_HD float2 cmul(float2 a, float2 b) {
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+FASTB_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+FASTB_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+FASTB_HD float2 cmuli(float2 a) { return make_float2(-a.y, a.x); }          // * (+i)
+
+// inverse radix-4: y_k = sum_n x_n i^(n k)
+FASTB_HD void dft4(float2& x0, float2& x1, float2& x2, float2& x3) {
+    const float2 s02 = cadd(x0, x2), d02 = csub(x0, x2);
+    const float2 s13 = cadd(x1, x3), d13 = cmuli(csub(x1, x3));
+    x0 = cadd(s02, s13);
+    x2 = csub(s02, s13);
+    x1 = cadd(d02, d13);
+    x3 = csub(d02, d13);
+}
+
+FASTB_HD void dft2(float2& x0, float2& x1) {
+    const float2 s = cadd(x0, x1), d = csub(x0, x1);
+    x0 = s;
+    x1 = d;
+}
+
+#define FASTB_C8 0.70710678118654752f
+#define FASTB_C16 0.92387953251128674f
+#define FASTB_S16 0.38268343236508977f
+
+// inverse 8-point DFT, natural order in and out (n = n1 + 2 n2, k = k2 + 4 k1)
+FASTB_HD void dft8(float2 (&v)[8]) {
+    dft4(v[0], v[2], v[4], v[6]);        // n1 = 0 : y[0][k2] in v[2 k2]
+    dft4(v[1], v[3], v[5], v[7]);        // n1 = 1 : y[1][k2] in v[2 k2 + 1]
+    // twiddle y[1][k2] *= w8^k2
+    v[3] = cmul(v[3], make_float2(FASTB_C8, FASTB_C8));
+    v[5] = cmuli(v[5]);
+    v[7] = cmul(v[7], make_float2(-FASTB_C8, FASTB_C8));
+    float2 o[8];
+#pragma unroll
+    for (int k2 = 0; k2 < 4; ++k2) {
+        o[k2] = cadd(v[2 * k2], v[2 * k2 + 1]);
+        o[k2 + 4] = csub(v[2 * k2], v[2 * k2 + 1]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = o[i];
+}
+
+// inverse 16-point DFT, natural order in and out (n = n1 + 4 n2, k = k2 + 4 k1)
+FASTB_HD void dft16(float2 (&v)[16]) {
+#pragma unroll
+    for (int n1 = 0; n1 < 4; ++n1) dft4(v[n1], v[n1 + 4], v[n1 + 8], v[n1 + 12]);  // -> v[n1+4k2]
+    // twiddles w16^(n1 k2)
+    v[5] = cmul(v[5], make_float2(FASTB_C16, FASTB_S16));      // (1,1) w^1
+    v[9] = cmul(v[9], make_float2(FASTB_C8, FASTB_C8));        // (1,2) w^2
+    v[13] = cmul(v[13], make_float2(FASTB_S16, FASTB_C16));    // (1,3) w^3
+    v[6] = cmul(v[6], make_float2(FASTB_C8, FASTB_C8));        // (2,1) w^2
+    v[10] = cmuli(v[10]);                                      // (2,2) w^4 = i
+    v[14] = cmul(v[14], make_float2(-FASTB_C8, FASTB_C8));     // (2,3) w^6
+    v[7] = cmul(v[7], make_float2(FASTB_S16, FASTB_C16));      // (3,1) w^3
+    v[11] = cmul(v[11], make_float2(-FASTB_C8, FASTB_C8));     // (3,2) w^6
+    v[15] = cmul(v[15], make_float2(-FASTB_C16, -FASTB_S16));  // (3,3) w^9
+    float2 o[16];
+#pragma unroll
+    for (int k2 = 0; k2 < 4; ++k2) {
+        float2 a = v[4 * k2], b = v[4 * k2 + 1], c = v[4 * k2 + 2], d = v[4 * k2 + 3];
+        dft4(a, b, c, d);                                       // over n1 -> k1
+        o[k2] = a;
+        o[k2 + 4] = b;
+        o[k2 + 8] = c;
+        o[k2 + 12] = d;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = o[i];
+}
+
+template <int LOG2N>
+struct LineFFT {
+    static constexpr int N = 1 << LOG2N;
+    static constexpr int S1 = N / 16;                       // threads per line
+    static constexpr bool kThree = (S1 >= 16);              // N >= 256
+    static constexpr int S2 = kThree ? S1 / 16 : 1;
+    static constexpr int SF = kThree ? S2 : S1;             // length of the last small DFTs
+    static constexpr bool kHasC = (SF > 1);
+    static constexpr int kPadA = kThree ? S2 : 0;
+    static constexpr int kBufA = 16 * (S1 + kPadA);         // exchange A layout: a*(S1+pad)+t
+    static constexpr int kBufC = 17 * S1;                   // exchange C layout: u*17 + e
+    static constexpr int kBuf = (kBufA > kBufC) ? kBufA : kBufC;   // float2 per line
+    static_assert(LOG2N >= 6 && LOG2N <= 11, "N must be 64..2048");
+
+    // element index held in register m of thread t before phase A
+    FASTB_HD static int n_in(int t, int m) { return t + S1 * m; }
+
+    // phase A: dft16 over m, twiddle, write exchange buffer.  tw[j] = exp(+2 pi i j / N)
+    FASTB_HD static void phase_a(int t, float2 (&v)[16], const float2* tw, float2* buf) {
+        dft16(v);
+#pragma unroll
+        for (int a = 1; a < 16; ++a) v[a] = cmul(v[a], tw[(t * a) & (N - 1)]);
+        if (kThree) {
+#pragma unroll
+            for (int a = 0; a < 16; ++a) buf[a * (S1 + kPadA) + t] = v[a];
+        } else {
+#pragma unroll
+            for (int a = 0; a < 16; ++a) buf[t * 17 + a] = v[a];
+        }
+    }
+
+    // phase B (N >= 256): gather, dft16 over m2, twiddle.  If S2 > 1 the caller must sync
+    // and then call phase_b_store before phase C.
+    FASTB_HD static void phase_b(int u, float2 (&v)[16], const float2* tw, const float2* buf) {
+        const int a = u / S2, t2 = u % S2;
+#pragma unroll
+        for (int m2 = 0; m2 < 16; ++m2) v[m2] = buf[a * (S1 + kPadA) + t2 + S2 * m2];
+        dft16(v);
+        if (S2 > 1) {
+#pragma unroll
+            for (int a2 = 1; a2 < 16; ++a2) v[a2] = cmul(v[a2], tw[(16 * t2 * a2) & (N - 1)]);
+        }
+    }
+
+    FASTB_HD static void phase_b_store(int u, const float2 (&v)[16], float2* buf) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) buf[u * 17 + e] = v[e];
+    }
+
+    // phase C: 16/SF DFTs of length SF across the SF threads of a group
+    FASTB_HD static void phase_c(int u, float2 (&v)[16], const float2* buf) {
+        constexpr int G = 16 / SF;
+        const int g0 = (u / SF) * SF, j = u % SF;
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+#pragma unroll
+            for (int t2 = 0; t2 < SF; ++t2) v[i * SF + t2] = buf[(g0 + t2) * 17 + i * SF + j];
+        }
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+            if (SF == 2) {
+                dft2(v[i * SF], v[i * SF + 1]);
+            } else if (SF == 4) {
+                dft4(v[i * SF], v[i * SF + 1], v[i * SF + 2], v[i * SF + 3]);
+            } else if (SF == 8) {
+                float2 w[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) w[q] = v[i * SF + q];
+                dft8(w);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[i * SF + q] = w[q];
+            }
+        }
+    }
+
+    // output index k held in register e of thread u after the last phase
+    FASTB_HD static int k_out(int u, int e) {
+        if (kThree) {
+            if (S2 == 1) return u + 16 * e;
+            const int a = u / S2, j = u % S2, i = e / S2, b2 = e % S2;
+            return a + 16 * (i * S2 + j) + 256 * b2;
+        }
+        const int j = u % SF, i = e / SF, b = e % SF;
+        return (i * SF + j) + 16 * b;
+    }
+};
+
+}  // namespace fastb

@@ -1,0 +1,485 @@
+// K2: phase-screen synthesis fused with the fibre-overlap detector.  Contract: include/fastb.h.
+//
+// One persistent CTA owns one complex transform ("pair" = two realisations) at a time:
+//   pass 1  for every frequency row r': white noise (Philox + Box-Muller in registers, or the
+//           caller's noise) x weight -> N-point line FFT in registers -> keep the n_pup output
+//           columns of the pupil crop -> CTA-private scratch T[c][r'] (L2 resident)
+//   pass 2  for every kept column c: N-point line FFT over r' -> keep the n_pup rows of the crop
+//           -> U (cos phi, sin phi) accumulated in registers for Re and Im screens
+//   final   fixed-order block reduction, exp(chi), normalisation -> 1 scalar per realisation.
+// Signs: the weight carries (-1)^(r'+c') and the output (-1)^(r+c), which turns the reference's
+// centred (fftshift-ed) inverse DFT (fast/funcs.py:218 via aotools.ift2) into a plain one.
+#include "fastb_common.cuh"
+#include "fft_core.cuh"
+
+namespace fastb {
+namespace {
+
+constexpr int kThreads = 256;
+
+struct RunArgs {
+    int n, n_pup, lo, coherent;
+    long long n_pairs, first_pair, ppc;
+    unsigned long long seed;
+    float inv_usum, sigma_chi;
+    const float* weight;      // N*N signed weight
+    const float* u_t;         // n_pup*n_pup, transposed: u_t[c*n_pup + r]
+    const float* chi;         // global-index log-amplitudes or NULL
+    const float2* noise;      // n_pairs*N*N or NULL
+    float* out_a;
+    float* out_b;
+    float2* scratch;          // gridDim.x slots of n*n_pup float2
+    int rows_per_block;       // direct kernel only
+};
+
+__device__ __forceinline__ void fast_sincos(float x, float* s, float* c) {
+    const float k = rintf(x * 0.15915494309189535f);
+    float r = fmaf(-k, 6.2831854820251465f, x);
+    r = fmaf(-k, -1.7484556000744883e-07f, r);
+    *s = __sinf(r);
+    *c = __cosf(r);
+}
+
+// accumulate U exp(i phi) for the two screens carried by one complex sample
+__device__ __forceinline__ void accumulate(float2 phi, float u, bool negate, float (&acc)[4]) {
+    if (negate) {
+        phi.x = -phi.x;
+        phi.y = -phi.y;
+    }
+    float s, c;
+    fast_sincos(phi.x, &s, &c);
+    acc[0] = fmaf(u, c, acc[0]);
+    acc[1] = fmaf(u, s, acc[1]);
+    fast_sincos(phi.y, &s, &c);
+    acc[2] = fmaf(u, c, acc[2]);
+    acc[3] = fmaf(u, s, acc[3]);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// fixed-order reduction of the 4 accumulators over the CTA, then the per-pair epilogue
+__device__ void finish_pair(const RunArgs& a, long long pair, float (&acc)[4], float* red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i] = warp_sum(acc[i]);
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) red[warp * 4 + i] = acc[i];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int w = 0; w < kThreads / 32; ++w)
+            for (int i = 0; i < 4; ++i) t[i] += red[w * 4 + i];
+        const long long g = a.first_pair + pair;
+        const long long chunk = g / a.ppc, pp = g % a.ppc;
+        const long long ia = chunk * 2 * a.ppc + pp, ib = ia + a.ppc;
+        float chia, chib;
+        if (a.chi) {
+            chia = a.chi[ia];
+            chib = a.chi[ib];
+        } else {
+            chia = a.sigma_chi * chi_normal(a.seed, (uint64_t)ia);
+            chib = a.sigma_chi * chi_normal(a.seed, (uint64_t)ib);
+        }
+        const float ea = expf(chia) * a.inv_usum, eb = expf(chib) * a.inv_usum;
+        const float zar = ea * t[0], zai = ea * t[1], zbr = eb * t[2], zbi = eb * t[3];
+        if (a.coherent) {
+            a.out_a[2 * pair] = zar;
+            a.out_a[2 * pair + 1] = zai;
+            a.out_b[2 * pair] = zbr;
+            a.out_b[2 * pair + 1] = zbi;
+        } else {
+            a.out_a[pair] = zar * zar + zai * zai;
+            a.out_b[pair] = zbr * zbr + zbi * zbi;
+        }
+    }
+    __syncthreads();
+}
+
+template <int S1>
+__device__ __forceinline__ void line_sync() {
+    if (S1 > 32) __syncthreads();
+    else __syncwarp();
+}
+
+// run phases A..C of the line FFT on v (see fft_core.cuh); u = thread index within the line
+template <int LOG2N>
+__device__ __forceinline__ void line_fft(int u, float2 (&v)[16], const float2* tw, float2* buf) {
+    using F = LineFFT<LOG2N>;
+    F::phase_a(u, v, tw, buf);
+    line_sync<F::S1>();
+    if (F::kThree) {
+        F::phase_b(u, v, tw, buf);
+        if (F::S2 > 1) {
+            line_sync<F::S1>();
+            F::phase_b_store(u, v, buf);
+            line_sync<F::S1>();
+            F::phase_c(u, v, buf);
+        }
+    } else {
+        F::phase_c(u, v, buf);
+    }
+    line_sync<F::S1>();          // buffer may be rewritten by the next line
+}
+
+template <int LOG2N, bool RNG>
+__global__ void __launch_bounds__(kThreads, 2) screen_detect_radix(const __grid_constant__ RunArgs a) {
+    using F = LineFFT<LOG2N>;
+    constexpr int N = F::N, S1 = F::S1, LPB = kThreads / S1;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* tw = reinterpret_cast<float2*>(smem_raw);
+    float2* bufs = tw + N;
+    const int pitch = a.n_pup | 1;
+    float2* tile = bufs + LPB * F::kBuf;
+    float* red = reinterpret_cast<float*>(tile + LPB * pitch);
+
+    const int tid = threadIdx.x;
+    const int ln = tid / S1, u = tid % S1;
+    float2* buf = bufs + ln * F::kBuf;
+    const int P = a.n_pup, lo = a.lo;
+
+    for (int j = tid; j < N; j += kThreads) {
+        double s, c;
+        sincospi(2.0 * (double)j / (double)N, &s, &c);
+        tw[j] = make_float2((float)c, (float)s);
+    }
+    __syncthreads();
+
+    float2* T = a.scratch + (size_t)blockIdx.x * N * P;
+    const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
+
+    for (long long pair = blockIdx.x; pair < a.n_pairs; pair += gridDim.x) {
+        const unsigned long long g = (unsigned long long)(a.first_pair + pair);
+        // ---------------- pass 1: rows ----------------
+        for (int row0 = 0; row0 < N; row0 += LPB) {
+            const int r = row0 + ln;
+            float2 v[16];
+            const float* wrow = a.weight + (size_t)r * N;
+            if (RNG) {
+#pragma unroll
+                for (int m = 0; m < 8; ++m) {
+                    const int j = u + S1 * m;
+                    const uint4 w = philox4x32_10((uint32_t)(r * (N / 2) + j), (uint32_t)g,
+                                                  (uint32_t)(g >> 32), kStreamNoise, k0, k1);
+                    const float2 n0 = box_muller(w.x, w.y), n1 = box_muller(w.z, w.w);
+                    const float w0 = __ldg(wrow + j), w1 = __ldg(wrow + j + N / 2);
+                    v[m] = make_float2(n0.x * w0, n0.y * w0);
+                    v[m + 8] = make_float2(n1.x * w1, n1.y * w1);
+                }
+            } else {
+                const float2* nrow = a.noise + ((size_t)pair * N + r) * N;
+#pragma unroll
+                for (int m = 0; m < 16; ++m) {
+                    const int j = u + S1 * m;
+                    const float2 nz = __ldg(nrow + j);
+                    const float w0 = __ldg(wrow + j);
+                    v[m] = make_float2(nz.x * w0, nz.y * w0);
+                }
+            }
+            line_fft<LOG2N>(u, v, tw, buf);
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                const int c = F::k_out(u, e) - lo;
+                if (c >= 0 && c < P) tile[ln * pitch + c] = v[e];
+            }
+            __syncthreads();
+            for (int idx = tid; idx < P * LPB; idx += kThreads) {
+                const int c = idx / LPB, l2 = idx % LPB;
+                __stcg(&T[(size_t)c * N + row0 + l2], tile[l2 * pitch + c]);
+            }
+            __syncthreads();
+        }
+        // ---------------- pass 2: columns + detector ----------------
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int col0 = 0; col0 < P; col0 += LPB) {
+            const int c = col0 + ln;
+            const bool active = c < P;
+            float2 v[16];
+            const float2* tcol = T + (size_t)(active ? c : 0) * N;
+#pragma unroll
+            for (int m = 0; m < 16; ++m) v[m] = __ldcg(tcol + u + S1 * m);
+            line_fft<LOG2N>(u, v, tw, buf);
+            if (active) {
+                const float* ucol = a.u_t + (size_t)c * P;
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    const int k = F::k_out(u, e);
+                    const int rr = k - lo;
+                    if (rr >= 0 && rr < P) accumulate(v[e], __ldg(ucol + rr), ((k + c + lo) & 1) != 0, acc);
+                }
+            }
+        }
+        finish_pair(a, pair, acc, red);
+    }
+}
+
+// ---- general even N: pruned direct DFT (slow path; also used for N not a power of two) ----
+template <bool RNG>
+__global__ void __launch_bounds__(kThreads) screen_detect_direct(const __grid_constant__ RunArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int N = a.n, P = a.n_pup, lo = a.lo, R = a.rows_per_block;
+    float2* tw = reinterpret_cast<float2*>(smem_raw);
+    float2* rows = tw + N;                       // R x N coloured noise
+    float* red = reinterpret_cast<float*>(rows + (size_t)R * N);
+    const int tid = threadIdx.x;
+
+    for (int j = tid; j < N; j += kThreads) {
+        double s, c;
+        sincospi(2.0 * (double)j / (double)N, &s, &c);
+        tw[j] = make_float2((float)c, (float)s);
+    }
+    __syncthreads();
+
+    float2* T = a.scratch + (size_t)blockIdx.x * N * P;
+    const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
+    const int half = N / 2;
+
+    for (long long pair = blockIdx.x; pair < a.n_pairs; pair += gridDim.x) {
+        const unsigned long long g = (unsigned long long)(a.first_pair + pair);
+        for (int row0 = 0; row0 < N; row0 += R) {
+            const int nr = min(R, N - row0);
+            if (RNG) {
+                for (int idx = tid; idx < nr * half; idx += kThreads) {
+                    const int rl = idx / half, j = idx % half, r = row0 + rl;
+                    const uint4 w = philox4x32_10((uint32_t)(r * half + j), (uint32_t)g,
+                                                  (uint32_t)(g >> 32), kStreamNoise, k0, k1);
+                    const float2 n0 = box_muller(w.x, w.y), n1 = box_muller(w.z, w.w);
+                    const float w0 = a.weight[(size_t)r * N + j], w1 = a.weight[(size_t)r * N + j + half];
+                    rows[rl * N + j] = make_float2(n0.x * w0, n0.y * w0);
+                    rows[rl * N + j + half] = make_float2(n1.x * w1, n1.y * w1);
+                }
+            } else {
+                for (int idx = tid; idx < nr * N; idx += kThreads) {
+                    const int rl = idx / N, j = idx % N, r = row0 + rl;
+                    const float2 nz = a.noise[((size_t)pair * N + r) * N + j];
+                    const float w0 = a.weight[(size_t)r * N + j];
+                    rows[rl * N + j] = make_float2(nz.x * w0, nz.y * w0);
+                }
+            }
+            __syncthreads();
+            for (int idx = tid; idx < nr * P; idx += kThreads) {
+                const int rl = idx / P, c = idx % P;
+                const int kk = c + lo;                 // output column, 0 <= kk < N
+                int ti = 0;
+                float sr = 0.f, si = 0.f;
+                const float2* row = rows + rl * N;
+                for (int cp = 0; cp < N; ++cp) {
+                    const float2 x = row[cp], t = tw[ti];
+                    sr = fmaf(x.x, t.x, fmaf(-x.y, t.y, sr));
+                    si = fmaf(x.x, t.y, fmaf(x.y, t.x, si));
+                    ti += kk;
+                    if (ti >= N) ti -= N;
+                }
+                T[(size_t)c * N + row0 + rl] = make_float2(sr, si);
+            }
+            __syncthreads();
+        }
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int idx = tid; idx < P * P; idx += kThreads) {
+            const int c = idx / P, rr = idx % P;
+            const int kk = rr + lo;
+            const float2* col = T + (size_t)c * N;
+            int ti = 0;
+            float sr = 0.f, si = 0.f;
+            for (int rp = 0; rp < N; ++rp) {
+                const float2 x = __ldcg(col + rp), t = tw[ti];
+                sr = fmaf(x.x, t.x, fmaf(-x.y, t.y, sr));
+                si = fmaf(x.x, t.y, fmaf(x.y, t.x, si));
+                ti += kk;
+                if (ti >= N) ti -= N;
+            }
+            accumulate(make_float2(sr, si), a.u_t[(size_t)c * P + rr], ((kk + c + lo) & 1) != 0, acc);
+        }
+        finish_pair(a, pair, acc, red);
+    }
+}
+
+__global__ void transpose_u_kernel(const float* __restrict__ U, int P, float* __restrict__ u_t) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P * P) return;
+    const int r = i / P, c = i % P;
+    u_t[(size_t)c * P + r] = U[i];
+}
+
+__global__ void rng_dump_kernel(unsigned long long seed, unsigned long long g, int N, float2* tile,
+                                long long chi_first, long long chi_count, float* chi) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int half = N / 2;
+    if (tile && i < (long long)N * half) {
+        const int r = (int)(i / half), j = (int)(i % half);
+        const uint4 w = philox4x32_10((uint32_t)(r * half + j), (uint32_t)g, (uint32_t)(g >> 32),
+                                      kStreamNoise, (uint32_t)seed, (uint32_t)(seed >> 32));
+        tile[(size_t)r * N + j] = box_muller(w.x, w.y);
+        tile[(size_t)r * N + j + half] = box_muller(w.z, w.w);
+    }
+    if (chi && i < chi_count) chi[i] = chi_normal(seed, (uint64_t)(chi_first + i));
+}
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+template <int LOG2N>
+size_t radix_smem_bytes(int n_pup) {
+    using F = LineFFT<LOG2N>;
+    const int LPB = kThreads / F::S1;
+    return sizeof(float2) * ((size_t)F::N + (size_t)LPB * F::kBuf + (size_t)LPB * (n_pup | 1)) +
+           sizeof(float) * 4 * (kThreads / 32);
+}
+
+int direct_rows(int n) {
+    int r = (int)((96 * 1024) / ((size_t)n * sizeof(float2)));
+    return r < 1 ? 1 : (r > 8 ? 8 : r);
+}
+size_t direct_smem_bytes(int n) {
+    return sizeof(float2) * ((size_t)n + (size_t)direct_rows(n) * n) + sizeof(float) * 4 * (kThreads / 32);
+}
+
+bool radix_ok(int n) { return n >= 64 && n <= 2048 && (n & (n - 1)) == 0; }
+
+int sm_count(int* out) {
+    int dev = 0;
+    FASTB_CUDA(cudaGetDevice(&dev));
+    FASTB_CUDA(cudaDeviceGetAttribute(out, cudaDevAttrMultiProcessorCount, dev));
+    return FASTB_OK;
+}
+
+constexpr int kMaxCtasPerSm = 4;
+
+template <int LOG2N>
+int launch_radix(const RunArgs& args, bool rng, int max_grid, cudaStream_t st) {
+    const size_t smem = radix_smem_bytes<LOG2N>(args.n_pup);
+    auto kern = rng ? screen_detect_radix<LOG2N, true> : screen_detect_radix<LOG2N, false>;
+    FASTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0, sms = 0;
+    FASTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
+    if (per_sm < 1) {
+        set_error("screen_detect_radix: kernel does not fit (smem %zu B)", smem);
+        return FASTB_ERR_UNSUPPORTED;
+    }
+    if (per_sm > kMaxCtasPerSm) per_sm = kMaxCtasPerSm;
+    int rc = sm_count(&sms);
+    if (rc) return rc;
+    long long grid = (long long)per_sm * sms;
+    if (grid > args.n_pairs) grid = args.n_pairs;
+    if (grid > max_grid) grid = max_grid;
+    kern<<<(unsigned)grid, kThreads, smem, st>>>(args);
+    return check_launch("screen_detect_radix");
+}
+
+}  // namespace
+}  // namespace fastb
+
+using namespace fastb;
+
+static int validate_run(const FastbRunParams* p) {
+    FASTB_REQUIRE(p, "fastb_screen_detect: NULL params");
+    FASTB_REQUIRE(p->n >= 4 && (p->n % 2) == 0, "fastb_screen_detect: n=%d must be even and >= 4", p->n);
+    FASTB_REQUIRE(p->n_pup >= 1 && p->n_pup <= p->n, "fastb_screen_detect: n_pup=%d outside 1..n", p->n_pup);
+    FASTB_REQUIRE(p->lo >= 0 && p->lo + p->n_pup <= p->n, "fastb_screen_detect: crop [%d,%d) outside grid",
+                  p->lo, p->lo + p->n_pup);
+    FASTB_REQUIRE(p->n_pairs >= 0 && p->first_pair >= 0, "fastb_screen_detect: negative pair range");
+    FASTB_REQUIRE(p->pairs_per_chunk > 0, "fastb_screen_detect: pairs_per_chunk must be > 0");
+    FASTB_REQUIRE(p->algo >= FASTB_ALGO_AUTO && p->algo <= FASTB_ALGO_RADIX, "fastb_screen_detect: bad algo");
+    FASTB_REQUIRE(p->u_sum != 0.0, "fastb_screen_detect: u_sum is zero");
+    if (p->algo == FASTB_ALGO_RADIX && !radix_ok(p->n)) {
+        set_error("fastb_screen_detect: radix path needs N = 64..2048 power of two, got %d", p->n);
+        return FASTB_ERR_UNSUPPORTED;
+    }
+    if (p->n > 4096) {
+        set_error("fastb_screen_detect: N=%d > 4096 not supported", p->n);
+        return FASTB_ERR_UNSUPPORTED;
+    }
+    return FASTB_OK;
+}
+
+extern "C" int64_t fastb_screen_detect_workspace_bytes(const FastbRunParams* p) {
+    if (validate_run(p)) return -1;
+    int sms = 0;
+    if (sm_count(&sms)) return -1;
+    long long grid = (long long)sms * kMaxCtasPerSm;
+    if (grid > p->n_pairs) grid = p->n_pairs;
+    if (grid < 1) grid = 1;
+    const size_t ut = align_up(sizeof(float) * (size_t)p->n_pup * p->n_pup, 256);
+    return (int64_t)(ut + (size_t)grid * p->n * p->n_pup * sizeof(float2));
+}
+
+extern "C" int fastb_screen_detect(const FastbRunParams* p, const float* d_weight, const float* d_U,
+                                   const float* d_chi, const float* d_noise, float* d_out_a,
+                                   float* d_out_b, void* d_workspace, int64_t workspace_bytes,
+                                   void* stream) {
+    int rc = validate_run(p);
+    if (rc) return rc;
+    FASTB_REQUIRE(d_weight && d_U && d_out_a && d_out_b && d_workspace, "fastb_screen_detect: NULL pointer");
+    if (p->n_pairs == 0) return FASTB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t ut = align_up(sizeof(float) * (size_t)p->n_pup * p->n_pup, 256);
+    const size_t slot = (size_t)p->n * p->n_pup * sizeof(float2);
+    FASTB_REQUIRE(workspace_bytes >= (int64_t)(ut + slot), "fastb_screen_detect: workspace too small (%lld B)",
+                  (long long)workspace_bytes);
+    long long max_grid = (long long)(((size_t)workspace_bytes - ut) / slot);
+    if (max_grid > (1 << 20)) max_grid = 1 << 20;
+
+    RunArgs a;
+    a.n = p->n;
+    a.n_pup = p->n_pup;
+    a.lo = p->lo;
+    a.coherent = p->coherent;
+    a.n_pairs = p->n_pairs;
+    a.first_pair = p->first_pair;
+    a.ppc = p->pairs_per_chunk;
+    a.seed = p->seed;
+    a.inv_usum = (float)(1.0 / p->u_sum);
+    a.sigma_chi = p->sigma_chi;
+    a.weight = d_weight;
+    a.u_t = (const float*)d_workspace;
+    a.chi = d_chi;
+    a.noise = (const float2*)d_noise;
+    a.out_a = d_out_a;
+    a.out_b = d_out_b;
+    a.scratch = (float2*)((char*)d_workspace + ut);
+    a.rows_per_block = direct_rows(p->n);
+
+    const int pp = p->n_pup * p->n_pup;
+    transpose_u_kernel<<<(pp + 255) / 256, 256, 0, st>>>(d_U, p->n_pup, (float*)d_workspace);
+    if ((rc = check_launch("transpose_u_kernel"))) return rc;
+
+    const bool rng = d_noise == nullptr;
+    const bool use_radix = p->algo == FASTB_ALGO_RADIX || (p->algo == FASTB_ALGO_AUTO && radix_ok(p->n));
+    if (use_radix) {
+        switch (p->n) {
+            case 64: return launch_radix<6>(a, rng, (int)max_grid, st);
+            case 128: return launch_radix<7>(a, rng, (int)max_grid, st);
+            case 256: return launch_radix<8>(a, rng, (int)max_grid, st);
+            case 512: return launch_radix<9>(a, rng, (int)max_grid, st);
+            case 1024: return launch_radix<10>(a, rng, (int)max_grid, st);
+            case 2048: return launch_radix<11>(a, rng, (int)max_grid, st);
+            default: break;
+        }
+    }
+    const size_t smem = direct_smem_bytes(p->n);
+    auto kern = rng ? screen_detect_direct<true> : screen_detect_direct<false>;
+    FASTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int sms = 0;
+    if ((rc = sm_count(&sms))) return rc;
+    long long grid = 2LL * sms;
+    if (grid > p->n_pairs) grid = p->n_pairs;
+    if (grid > max_grid) grid = max_grid;
+    kern<<<(unsigned)grid, kThreads, smem, st>>>(a);
+    return check_launch("screen_detect_direct");
+}
+
+extern "C" int fastb_rng_dump(uint64_t seed, int64_t pair, int32_t n, float* d_noise_tile,
+                              int64_t chi_first, int64_t chi_count, float* d_chi_normals, void* stream) {
+    FASTB_REQUIRE(n >= 2 && (n % 2) == 0, "fastb_rng_dump: n must be even");
+    FASTB_REQUIRE(pair >= 0 && chi_first >= 0 && chi_count >= 0, "fastb_rng_dump: negative index");
+    long long work = d_noise_tile ? (long long)n * (n / 2) : 0;
+    if (d_chi_normals && chi_count > work) work = chi_count;
+    if (work == 0) return FASTB_OK;
+    rng_dump_kernel<<<(unsigned)((work + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        seed, (unsigned long long)pair, n, (float2*)d_noise_tile, chi_first, chi_count, d_chi_normals);
+    return check_launch("rng_dump_kernel");
+}

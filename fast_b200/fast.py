@@ -1,0 +1,569 @@
+"""`Fast` / `FastResult`: the reference's public object protocol (fast/fast.py:20-140,931-1002)
+over the B200 CUDA library.
+
+    import fast_b200 as fast
+    sim = fast.Fast(p)          # p: dict or path to a .py config, same keys as ojdf/fast
+    res = sim.run()             # FastResult: .power .dB_rel .dB_abs .dBm .scintillation_index
+
+What runs where
+  host (numpy, once per config): config, geometry scalars, pupil and fibre mode, link budget
+  device (libfastb.so):          residual-PSD build + Simpson integrals + pupil filter
+                                 (fastb_psd_build / fastb_simpson2d / fastb_pupil_filter),
+                                 noise -> screens -> detector (fastb_screen_detect),
+                                 result statistics (fastb_stats)
+There is no CPU fallback for the device part.
+"""
+import logging
+import math
+
+import numpy
+import torch
+
+from . import _lib
+from . import ao_power_spectra
+from . import conf
+from . import dist
+from . import funcs
+
+logger = logging.getLogger(__name__)
+
+_AO_MODES = {'NOAO': _lib.AO_NOAO, 'AO': _lib.AO_AO, 'TT': _lib.AO_AO, 'LGSAO': _lib.AO_LGSAO}
+
+
+class SpatialFrequencyStruct():
+    """Centred angular-frequency grid (fast/fast.py:877-921): fx[r, c] = fx_axis[c],
+    fy[r, c] = fy_axis[r].  2-D arrays are built on first use; the device never reads them."""
+
+    def __init__(self, fx_axis, fy_axis=None):
+        self.fx_axis = fx_axis
+        self.fy_axis = fx_axis if fy_axis is None else fy_axis
+        self.freq_per_layer = False
+        self.f = fx_axis
+        self.df = self.dfx = fx_axis[..., 1] - fx_axis[..., 0]
+        self.dfy = self.fy_axis[..., 1] - self.fy_axis[..., 0]
+        self._grid = None
+
+    def _mesh(self):
+        if self._grid is None:
+            self._grid = numpy.meshgrid(self.fx_axis, self.fy_axis)
+        return self._grid
+
+    @property
+    def fx(self):
+        return self._mesh()[0]
+
+    @property
+    def fy(self):
+        return self._mesh()[1]
+
+    @property
+    def fabs(self):
+        return numpy.sqrt(self.fx ** 2 + self.fy ** 2)
+
+
+class SpatialFrequencies():
+    """fast/fast.py:814-833: `main` grid with df = 2 pi / (N dx)."""
+
+    def __init__(self, N, dx):
+        self.N, self.dx = N, dx
+        self.main = SpatialFrequencyStruct(numpy.arange(-N / 2., N / 2.) * (2 * numpy.pi / (N * dx)))
+        self.f = self.main.f
+        self.df = self.main.df
+
+    fx = property(lambda self: self.main.fx)
+    fy = property(lambda self: self.main.fy)
+    fabs = property(lambda self: self.main.fabs)
+
+
+class Fast():
+    """Drop-in for `fast.Fast` on the Monte-Carlo path (fast/fast.py:20-140).
+
+    Readable attributes follow the reference: I, result, link_budget, diffraction_limit,
+    powerspec, powerspec_per_layer, logamp_powerspec, logamp_var, phs_var, phs_var_weights,
+    aniso_servo_error, alias_error, noise_error, fitting_error, r0, theta0, tau0, *_los,
+    pupil, pupil_mode, W0, dx, Npxls, Npxls_pup, freq, L, h, cn2, wind_vector, params.
+    Array-valued PSD attributes are fetched from the device on first access."""
+
+    def __init__(self, params):
+        self.conf = conf.ConfigParser(params)
+        self.params = self.conf.config
+
+        self.Niter = self.params['NITER']
+        self.Nchunks = self.params['NCHUNKS']
+        self.fftw = False                      # no FFTW on this path; the key is accepted
+        self.nthreads = self.params['FFTW_THREADS']
+        self.seed = self.params['SEED']
+        if self.seed != None:  # noqa: E711  (reference semantics: 0 is a valid seed)
+            self.set_seed(self.seed)
+        self.temporal = self.params['TEMPORAL']
+        self.dt = self.params['DT']
+        self.rng_mode = self.params.get('RNG', conf.EXTRA_DEFAULTS['RNG'])
+        if self.rng_mode not in ('device', 'numpy'):
+            raise Exception("RNG must be 'device' or 'numpy'")
+
+        if self.Niter % self.Nchunks != 0:
+            raise Exception('NCHUNKS must divide NITER without remainder')
+        self.Niter_per_chunk = self.Niter // self.Nchunks
+        if not (self.Niter_per_chunk % 2 == 0) and not self.temporal:
+            raise Exception('NITER/NCHUNKS must be even number')
+        if self.temporal:
+            raise NotImplementedError(
+                "TEMPORAL=True (frozen-flow time series, fast/fast.py:607-637) is not built on the "
+                "CUDA path yet; set TEMPORAL=False")
+        if self.params['SUBHARM']:
+            raise NotImplementedError(
+                "SUBHARM=True (fast/funcs.py:225-258) is not built on the CUDA path yet")
+
+        _lib.require_cuda()
+        dev = self.params.get('DEVICE', None)
+        self.device = torch.device(dev) if dev is not None else torch.device('cuda', torch.cuda.current_device())
+        self._d = {}                           # device tensors by name
+        self._host_cache = {}
+
+        self.init_logging()
+        self.init_atmos()
+        self.init_beam_params()
+        self.init_frequency_grid()
+        self.init_ao_params()
+        self.init_pupil_mask()
+        self.init_phs_logamp()
+        self.compute_link_budget()
+        self.compute_powerspec()
+        self.fftw_objs = None
+
+    # ------------------------------------------------------------------ init (host scalars)
+    def init_logging(self):
+        logging.basicConfig(filename=self.params['LOGFILE'],
+                            level=logging.getLevelName(self.params['LOGLEVEL']),
+                            format="[%(levelname)s] %(name)s.%(funcName)s | %(message)s")
+
+    def calc_zenith_correction(self, zenith_angle):
+        return 1 / numpy.cos(numpy.radians(zenith_angle))
+
+    def set_seed(self, seed):
+        funcs._R = numpy.random.default_rng(seed)
+
+    def init_atmos(self):
+        """Line-of-sight geometry per layer (fast/fast.py:229-276)."""
+        p = self.params
+        g = self.zenith_correction = self.calc_zenith_correction(p['ZENITH_ANGLE'])
+        self.h = p['H_TURB'] * g
+        self.cn2 = p['CN2_TURB'] * g
+        self.L = p['L_SAT'] if p['L_SAT'] != None else funcs.l_path(p['H_SAT'], p['ZENITH_ANGLE'])  # noqa: E711
+        self.dtheta = p['DTHETA']
+        self.paa = numpy.sqrt(self.dtheta[0] ** 2 + self.dtheta[1] ** 2)
+
+        self.wind_dir = p['WIND_DIR']
+        if 'AZIMUT_SAT' in p:
+            # modulus 380 is the reference's (fast/fast.py:250); kept for parity
+            self.wind_dir = [(x - p['AZIMUT_SAT']) % 380 for x in self.wind_dir]
+        ang = numpy.radians(self.wind_dir)
+        self.wind_vector = (p['WIND_SPD'] * numpy.array([numpy.cos(ang), numpy.sin(ang) / g])).T
+        if 'ANISO_DL' in p:
+            self.wind_correction = funcs.calculate_wind_correction(self.h, p['ANISO_DL'], p['TLOOP'])
+            self.wind_vector = self.wind_vector + self.wind_correction
+        self.wind_speed = numpy.hypot(self.wind_vector[:, 0], self.wind_vector[:, 1])
+
+        def r0_of(cn2_sum, lam):
+            return (0.423 * (2 * numpy.pi / lam) ** 2 * cn2_sum) ** (-3. / 5.)
+
+        def theta0_of(cn2, h, lam):
+            return 0.057 * lam ** (6. / 5.) * numpy.sum(cn2 * h ** (5. / 3.)) ** (-3. / 5.)
+
+        def tau0_of(cn2, v, lam):
+            return float(numpy.sum(cn2 * v ** (5. / 3.)) ** (-3. / 5.) * 0.057 * lam ** (6. / 5.))
+
+        def rytov_of(cn2, h, lam):
+            return 2.25 * (2 * numpy.pi / lam) ** (7. / 6.) * numpy.sum(cn2 * h ** (5. / 6.))
+
+        cn2_0, h_0, w_0 = (numpy.asarray(p[k], dtype=float) for k in ('CN2_TURB', 'H_TURB', 'WIND_SPD'))
+        self.r0 = r0_of(cn2_0.sum(), 500e-9)
+        self.theta0 = theta0_of(cn2_0, h_0, 500e-9)
+        self.tau0 = tau0_of(cn2_0, w_0, 500e-9)
+        self.rytov_variance = rytov_of(cn2_0, h_0, 500e-9)
+        wvl = p['WVL']
+        self.r0_los = r0_of(self.cn2.sum(), wvl)
+        self.theta0_los = theta0_of(self.cn2, self.h, wvl)
+        self.tau0_los = tau0_of(self.cn2, self.wind_speed, wvl)
+        self.rytov_variance_los = rytov_of(self.cn2, self.h, wvl)
+        self.L0 = p['L0']
+        self.l0 = p['l0']
+
+    def init_beam_params(self):
+        p = self.params
+        self.power = p['POWER']
+        self.W0 = p['W0']
+        self.F0 = numpy.inf
+        self.wvl = p['WVL']
+        self.k = 2 * numpy.pi / self.wvl
+        self.D_ground, self.obsc_ground = p['D_GROUND'], p['OBSC_GROUND']
+        self.D_sat, self.obsc_sat = p['D_SAT'], p['OBSC_SAT']
+
+    def init_frequency_grid(self):
+        """DX / NPXLS 'auto' rules and the pupil window (fast/fast.py:147-227)."""
+        p = self.params
+        if p['DX'] == 'auto':
+            self.dx = numpy.min([p['DSUBAP'] / 2, self.r0_los / 2, self.D_ground / 10])
+            if p['AO_MODE'] == 'NOAO':
+                self.dx = self.r0_los / 2
+            logger.info(f"Auto set DX to {self.dx}")
+        else:
+            self.dx = p['DX']
+
+        if p['NPXLS'] == 'auto':
+            nyq = numpy.min([numpy.pi / (self.h[-1] * self.paa / 206265.),       # anisoplanatism
+                             numpy.pi / (max(self.wind_speed) * p['TLOOP']),      # servo lag
+                             numpy.pi / p['DSUBAP'] / 5])                         # corrected region
+            n_nyq = int(2 * numpy.ceil(2 * numpy.pi / (nyq * self.dx) / 2))
+            n_ap = int(2 * numpy.ceil(p['D_GROUND'] / self.dx / 2)) + 2
+            self.Npxls = int(numpy.max([n_nyq, n_ap]))
+            logger.info(f"Auto set NPXLS to {self.Npxls}")
+            if p['AO_MODE'] == 'NOAO' and not numpy.isinf(p['L0']):
+                n_L0 = int(2 * numpy.ceil((p['L0'] * 2) / self.dx) / 2)
+                if n_L0 > self.Npxls:
+                    logger.warning(f"L0 set with NOAO mode, low orders may be undersampled. "
+                                   f"Recommended NPXLS: {n_L0}")
+        else:
+            self.Npxls = int(p['NPXLS'])
+        if self.Npxls % 2:
+            raise Exception('NPXLS must be even')
+        if self.Npxls > 2048:
+            logger.warning(f"NPXLS is large ({self.Npxls}) and may cause very high memory usage")
+        self.Npxls_pup = int(numpy.ceil(self.D_ground / self.dx)) + 2
+        if self.Npxls_pup > self.Npxls:
+            raise Exception('aperture does not fit in the grid: increase NPXLS or DX')
+        self.freq = SpatialFrequencies(self.Npxls, self.dx)
+        self.subharmonics = False
+
+    def init_ao_params(self):
+        p = self.params
+        self.ao_mode = p['AO_MODE']
+        if self.ao_mode not in _AO_MODES:
+            raise Exception('Mode not recognised, note that "AO_PA", "TT_PA" and "LGS_PA" are now '
+                            '"AO" and "TT" and "LGSAO')
+        self.Dsubap, self.tloop, self.texp = p['DSUBAP'], p['TLOOP'], p['TEXP']
+        self.Zmax, self.alias, self.noise = p['ZMAX'], p['ALIAS'], p['NOISE']
+        self.modal, self.modal_mult = p['MODAL'], p['MODAL_MULT']
+        if self.ao_mode == 'TT':
+            self.Zmax, self.modal, self.modal_mult = 3, True, 1   # tip/tilt = modal, Noll 1..3
+
+    @property
+    def lf_mask(self):
+        """Corrected-region mask as a host array (fast/fast.py:317-319).  Zonal masks are
+        recomputed on the device from fx, fy; modal ones are built here and uploaded."""
+        if 'lf_mask' not in self._host_cache:
+            self._host_cache['lf_mask'] = ao_power_spectra.mask_lf(
+                self.freq.main, self.Dsubap, modal=self.modal, modal_mult=self.modal_mult,
+                Zmax=self.Zmax, D=self.D_ground)
+        return self._host_cache['lf_mask']
+
+    @property
+    def hf_mask(self):
+        return 1 - self.lf_mask
+
+    def init_pupil_mask(self):
+        """Aperture, fibre mode, crop window (fast/fast.py:332-392); host numpy, once."""
+        N, dx = self.Npxls, self.dx
+        self.dx_sat = self.D_sat / 32
+        ptype = 'axicon' if self.params['AXICON'] else 'gauss'
+        pupil_full = funcs.compute_pupil(N, dx, self.D_ground, self.obsc_ground)
+        self.pupil_sat = funcs.compute_pupil(32, self.dx_sat, self.D_sat, self.obsc_sat)
+        mode_full, self.W0 = funcs.compute_gaussian_mode(pupil_full, dx, self.W0, D=self.D_ground,
+                                                         obsc=self.obsc_ground, ptype=ptype)
+        self.pupil_mode_sat, self.W0_sat = funcs.compute_gaussian_mode(self.pupil_sat, self.dx_sat,
+                                                                       "opt", ptype="gauss")
+        self._pm_full = pupil_full * mode_full            # input of the device pupil filter
+        lo, hi = (N - self.Npxls_pup) // 2, (N + self.Npxls_pup) // 2
+        self._lo = lo
+        self.pup_coords = numpy.array((numpy.arange(lo, hi), numpy.arange(lo, hi))).astype(int)
+        self.pupil = pupil_full[lo:hi, lo:hi]
+        self.pupil_mode = mode_full[lo:hi, lo:hi]
+        return self.pupil
+
+    def init_phs_logamp(self):
+        # screens are never materialised on this path; `logamp` holds the host draws in
+        # RNG='numpy' mode (fast/fast.py:440-443)
+        self.phs = None
+        self.logamp = numpy.zeros((self.Niter))
+
+    def compute_link_budget(self):
+        """Analytic link budget [dB] and the diffraction-limited power (fast/fast.py:670-734)."""
+        up = self.params['PROP_DIR'] == "up"
+        if up:
+            D_t, D_r, obsc_t, obsc_r = self.D_ground, self.D_sat, self.obsc_ground, self.obsc_sat
+            mode, dx_r, pupil_r, w0 = self.pupil_mode_sat, self.dx_sat, self.pupil_sat, self.W0
+        else:
+            D_t, D_r, obsc_t, obsc_r = self.D_sat, self.D_ground, self.obsc_sat, self.obsc_ground
+            mode, dx_r, pupil_r, w0 = self.pupil_mode, self.dx, self.pupil, self.W0_sat
+        lb = {}
+        lb['power'] = 10 * numpy.log10(self.power / 1e-3)
+        lb['free_space'] = 10 * numpy.log10((self.wvl / (4 * numpy.pi * self.L)) ** 2)
+        # truncated-Gaussian transmitter gain, Klein & Degnan, Appl. Opt. 13 (1974) eq. 9
+        alpha, gamma = D_t / (2 * w0), obsc_t / D_t
+        g_t = 2 / alpha ** 2 * (numpy.exp(-alpha ** 2) - numpy.exp(-gamma ** 2 * alpha ** 2)) ** 2
+        lb['transmitter_gain'] = 10 * numpy.log10((numpy.pi * D_t ** 2) * 4 * numpy.pi / self.wvl ** 2 * g_t)
+        area = numpy.pi * ((D_r / 2) ** 2 - (obsc_r / 2) ** 2)
+        lb['receiver_gain'] = 10 * numpy.log10(4 * numpy.pi * area / self.wvl ** 2)
+        lb['transmission_loss'] = 10 * numpy.log10(self.params['TRANSMISSION'])
+        lb['smf_coupling'] = 10 * numpy.log10(((pupil_r * mode).sum() * dx_r) ** 2 / (mode ** 2).sum())
+        self.link_budget = lb
+        self.diffraction_limit = 10 ** (sum(lb.values()) / 10) / 1e3      # W
+        return self.link_budget
+
+    # ------------------------------------------------------------------ K1 on the device
+    def _psd_params(self):
+        pp = _lib.PsdParams()
+        L = len(self.h)
+        if L > _lib.MAX_LAYERS:
+            raise Exception(f'at most {_lib.MAX_LAYERS} turbulence layers are supported')
+        pp.n, pp.n_layers = self.Npxls, L
+        pp.ao_mode = _AO_MODES[self.ao_mode]
+        pp.alias = 1 if self.alias else 0
+        pp.lmax = pp.kmax = 5
+        pp.df = float(self.freq.main.df)
+        pp.k, pp.wvl = float(self.k), float(self.wvl)
+        pp.L0, pp.l0 = float(self.L0), float(self.l0)
+        pp.dsubap, pp.tloop, pp.texp = float(self.Dsubap), float(self.tloop), float(self.texp)
+        pp.noise_var = float(self.noise)
+        pp.dtheta[0], pp.dtheta[1] = float(self.dtheta[0]), float(self.dtheta[1])
+        for i in range(L):
+            pp.h[i], pp.cn2[i] = float(self.h[i]), float(self.cn2[i])
+            pp.vx[i], pp.vy[i] = float(self.wind_vector[i, 0]), float(self.wind_vector[i, 1])
+        return pp
+
+    def compute_powerspec(self):
+        """Residual phase PSD, log-amplitude PSD and the error-budget integrals
+        (fast/fast.py:445-492) -- one fused kernel + one batched Simpson reduction."""
+        N, L, dev = self.Npxls, len(self.h), self.device
+        f64 = torch.float64
+        d = self._d
+        d['pupil_filter'] = _lib.pupil_filter(torch.from_numpy(numpy.ascontiguousarray(self._pm_full)).to(dev))
+        lf = zf = None
+        if self.modal:
+            lf = torch.from_numpy(numpy.ascontiguousarray(self.lf_mask, dtype=float)).to(dev)
+        if self.ao_mode == 'LGSAO':
+            fm = self.freq.main
+            z = ao_power_spectra.zernike_squared_filter(fm.fabs, fm.fx, fm.fy, self.D_ground, 4).real
+            zf = torch.from_numpy(numpy.ascontiguousarray(z)).to(dev)
+        # one slab: [aniso_servo, alias, fitting | noise | W | logamp | per-layer (L)]
+        slab = torch.zeros((6 + L, N, N), dtype=f64, device=dev)
+        d['turb'] = torch.empty((L, N, N), dtype=f64, device=dev)
+        d['g_ao'] = torch.empty((L, N, N), dtype=f64, device=dev)
+        d['alias'] = torch.empty((L, N, N), dtype=f64, device=dev)
+        d['weight'] = torch.empty((N, N), dtype=torch.float32, device=dev)
+        outs = {'integrands': slab[0:3], 'noise': slab[3], 'powerspec': slab[4], 'logamp': slab[5],
+                'powerspec_per_layer': slab[6:], 'turb': d['turb'], 'g_ao': d['g_ao'],
+                'alias': d['alias'], 'weight': d['weight']}
+        _lib.psd_build(self._psd_params(), outs, lf_mask=lf, zfilter=zf, pupil_filter=d['pupil_filter'])
+        d['noise'], d['powerspec'], d['logamp'], d['powerspec_per_layer'] = slab[3], slab[4], slab[5], slab[6:]
+        w = torch.from_numpy(funcs.simpson_weights(self.freq.main.f)).to(dev)
+        ints = _lib.simpson2d(slab, w).cpu().numpy()
+        noao = self.ao_mode == 'NOAO'
+        self.aniso_servo_error = float(ints[0])
+        self.alias_error = float(ints[1]) if (self.alias and not noao) else 0.
+        self.fitting_error = float(ints[2])
+        self.noise_error = float(ints[3]) if (self.noise > 0 and not noao) else 0.
+        self.phs_var = float(ints[4])
+        self.logamp_var = float(ints[5])
+        self.phs_var_weights = ints[6:] / self.phs_var
+        self.powerspec_subharm = self.phs_var_subharm = self.phs_var_weights_sh = None
+        self.temporal_powerspec = self.temporal_logamp_powerspec = None
+        self.shifts = self.shifts_sh = None
+        U = numpy.ascontiguousarray(self.pupil * self.pupil_mode)
+        self._u_sum = float(U.sum())
+        d['U'] = torch.from_numpy(U.astype(numpy.float32)).to(dev)
+
+    def _host(self, name):
+        if name not in self._host_cache:
+            self._host_cache[name] = self._d[name].cpu().numpy()
+        return self._host_cache[name]
+
+    powerspec = property(lambda self: self._host('powerspec'))
+    powerspec_per_layer = property(lambda self: self._host('powerspec_per_layer'))
+    logamp_powerspec = property(lambda self: self._host('logamp'))
+    turb_powerspec = property(lambda self: self._host('turb'))
+    pupil_filter = property(lambda self: self._host('pupil_filter'))
+
+    @property
+    def G_ao(self):
+        return 1 if self.ao_mode == 'NOAO' else self._host('g_ao')
+
+    @property
+    def alias_powerspec(self):
+        return self._host('alias') if (self.alias and self.ao_mode != 'NOAO') else 0.
+
+    @property
+    def noise_powerspec(self):
+        return self._host('noise') if (self.noise > 0 and self.ao_mode != 'NOAO') else 0.
+
+    # ------------------------------------------------------------------ K2 on the device
+    def _run_params(self, n_pairs, first_pair, algo=_lib.ALGO_AUTO):
+        rp = _lib.RunParams()
+        rp.n, rp.n_pup, rp.lo = self.Npxls, self.Npxls_pup, self._lo
+        rp.coherent = 1 if self.params['COHERENT'] else 0
+        rp.algo = algo
+        rp.n_pairs, rp.first_pair = int(n_pairs), int(first_pair)
+        rp.pairs_per_chunk = self.Niter_per_chunk // 2
+        rp.seed = int(self.seed) & 0xFFFFFFFFFFFFFFFF if self.seed != None else self._auto_seed()  # noqa: E711
+        rp.u_sum = self._u_sum
+        rp.sigma_chi = math.sqrt(self.logamp_var)
+        return rp
+
+    def _auto_seed(self):
+        if not hasattr(self, '_seed_drawn'):
+            self._seed_drawn = int(numpy.random.SeedSequence().generate_state(2, numpy.uint32).view(numpy.uint64)[0])
+        return self._seed_drawn
+
+    def _workspace(self, rp):
+        nbytes = _lib.screen_detect_workspace_bytes(rp)
+        ws = self._d.get('workspace')
+        if ws is None or ws.numel() < nbytes:
+            ws = self._d['workspace'] = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        return ws
+
+    def screen_detect(self, first_pair, n_pairs, noise=None, chi=None, algo=_lib.ALGO_AUTO):
+        """Run K2 for global pairs [first_pair, first_pair + n_pairs).  Returns two device
+        tensors (results of the Re and Im realisations); complex64 when COHERENT.
+        noise: optional (n_pairs, N, N) complex64 device tensor; chi: optional float32 device
+        tensor indexed by global realisation index."""
+        rp = self._run_params(n_pairs, first_pair, algo)
+        width = 2 if rp.coherent else 1
+        out_a = torch.empty(n_pairs * width, dtype=torch.float32, device=self.device)
+        out_b = torch.empty(n_pairs * width, dtype=torch.float32, device=self.device)
+        if n_pairs:
+            nz = None if noise is None else torch.view_as_real(noise.contiguous())
+            _lib.screen_detect(rp, self._d['weight'], self._d['U'], out_a, out_b, self._workspace(rp),
+                               chi=chi, noise=nz)
+        if rp.coherent:
+            out_a = torch.view_as_complex(out_a.view(-1, 2))
+            out_b = torch.view_as_complex(out_b.view(-1, 2))
+        return out_a, out_b
+
+    def compute_logamp(self):
+        """RNG='numpy': host draws in the reference's order (fast/fast.py:639-645);
+        RNG='device': chi is generated inside the kernel and this only clears the buffer."""
+        self.logamp[:] = 0
+        if self.rng_mode == 'numpy':
+            self.logamp[:] = funcs.generate_random_coefficients_logamp(self.Niter, self.logamp_var).real
+            self._d['chi'] = torch.from_numpy(self.logamp.astype(numpy.float32)).to(self.device)
+        else:
+            self._d.pop('chi', None)
+        return self.logamp
+
+    def compute_phs(self, chunk=0):
+        """RNG='numpy': draw this chunk's complex noise on the host exactly like the reference
+        (fast/fast.py:593) and stage it on the device.  Screens are not materialised."""
+        if self.rng_mode == 'numpy':
+            J2, N = self.Niter_per_chunk // 2, self.Npxls
+            rand = funcs.generate_random_coefficients((J2, N, N)).astype(numpy.complex64)
+            self._d['noise'] = torch.from_numpy(rand).to(self.device)
+        return None
+
+    def compute_detector(self, chunk=0):
+        """Screens + detector for one chunk on the device; returns the chunk's J results in
+        the reference's order [Re half | Im half] (fast/fast.py:647-668) as a device tensor."""
+        ppc = self.Niter_per_chunk // 2
+        noise = self._d.get('noise') if self.rng_mode == 'numpy' else None
+        a, b = self.screen_detect(chunk * ppc, ppc, noise=noise, chi=self._d.get('chi'))
+        self.random_iters = torch.cat([a, b])
+        return self.random_iters
+
+    def run(self):
+        """Monte-Carlo run (fast/fast.py:115-140).  With torch.distributed initialised and
+        RNG='device', pair ranges are sharded over the ranks and gathered (fast_b200/dist.py)."""
+        logger.debug("Compute log amplitude values")
+        self.compute_logamp()
+        ppc = self.Niter_per_chunk // 2
+        total = self.Nchunks * ppc
+        if self.rng_mode == 'device':
+            rank, world = dist.rank_world()
+            lo, hi = dist.shard_range(total, rank, world)
+            a, b = self.screen_detect(lo, hi - lo)
+            a, b = dist.gather_pairs(a, b, total, world)
+            flat = dist.assemble(a, b, self.Nchunks, ppc)
+        else:
+            parts = []
+            for i in range(self.Nchunks):
+                logger.debug(f"Compute phase for chunk {i+1}")
+                self.compute_phs(chunk=i)
+                logger.debug(f"Compute detector for chunk {i+1}")
+                parts.append(self.compute_detector(chunk=i))
+            flat = torch.cat(parts)
+            self._d.pop('noise', None)
+        self._d['result'] = flat
+        I = flat.cpu().numpy()
+        I = I.astype(complex) if self.params['COHERENT'] else I.astype(float)
+        self.result = FastResult(I, self.diffraction_limit)
+        self.I = self.result.power
+        logger.info(self.result)
+        return self.result
+
+    def result_stats(self, db_lo=-60.0, db_hi=3.0, nbins=4096):
+        """Moments / extrema / dB histogram of the last run computed on the device
+        (fastb_stats) and, under torch.distributed, all-reduced over the ranks' shards."""
+        r = self._d['result']
+        if r.is_complex():
+            r = (r.real ** 2 + r.imag ** 2).contiguous()
+        return dist.reduced_stats(r, db_lo, db_hi, nbins, already_global=True)
+
+    # ------------------------------------------------------------------ FITS (optional dep)
+    def make_header(self, params):
+        from astropy.io import fits
+        hdr = fits.Header()
+        for key, val in (('ZENITH', params['ZENITH_ANGLE']), ('WVL', int(params['WVL'] * 1e9)),
+                         ('OTRSCALE', str(params['L0']) if numpy.isinf(params['L0']) else params['L0']),
+                         ('INRSCALE', params['l0']), ('POWER', params['POWER']), ('PAA', self.paa),
+                         ('AO_MODE', self.ao_mode), ('TLOOP', params['TLOOP']), ('TEXP', params['TEXP']),
+                         ('DSUBAP', params['DSUBAP']), ('ALIAS', str(params['ALIAS'])),
+                         ('NOISE', params['NOISE']), ('D_GND', params['D_GROUND']),
+                         ('OBSC_GND', params['OBSC_GROUND']), ('D_SAT', params['D_SAT']),
+                         ('OBSC_SAT', params['OBSC_SAT']), ('AXICON', str(params['AXICON'])),
+                         ('W0', self.W0), ('L_SAT', self.L), ('H_SAT', params['H_SAT']), ('DX', self.dx),
+                         ('NPXLS', self.Npxls), ('NITER', self.Niter), ('R0', self.r0),
+                         ('THETA0', self.theta0), ('TAU0', self.tau0), ('DIFFLIM', self.diffraction_limit)):
+            hdr[key] = val
+        if self.seed != None:  # noqa: E711
+            hdr['SEED'] = self.seed
+        return hdr
+
+    def save(self, fname, **kwargs):
+        from astropy.io import fits
+        fits.writeto(fname, self.result.power, header=self.make_header(self.params), **kwargs)
+
+
+class FastResult():
+    """Unit conversions over the per-realisation array (fast/fast.py:931-994): `_r` is the
+    received power relative to the diffraction limit (complex field when COHERENT)."""
+
+    def __init__(self, random_iters, diffraction_limit, header=None):
+        self._r = random_iters
+        self._dl = diffraction_limit
+        if header != None:  # noqa: E711
+            self.hdr = header
+
+    dB_rel = property(lambda self: 10 * numpy.log10(self._r))
+    dB_abs = property(lambda self: 10 * numpy.log10(self._r * self._dl))
+    dBm = property(lambda self: 10 * numpy.log10(self._r * self._dl / 1e-3))
+    power = property(lambda self: self._dl * self._r)
+    scintillation_index = property(lambda self: (self._r / self._r.mean()).var())
+    avg_power_W = property(lambda self: self.power.mean())
+    avg_power_dBm = property(lambda self: 10 * numpy.log10(self.avg_power_W / 1e-3))
+    avg_power_dB_rel = property(lambda self: 10 * numpy.log10((self.power / self._dl).mean()))
+    avg_power_dB_abs = property(lambda self: 10 * numpy.log10(self.avg_power_W))
+
+    def __str__(self):
+        return ("FAST result statistics:\n"
+                f"            Avg. power (W): {self.avg_power_W}\n"
+                f"            Avg. power (dBm): {self.avg_power_dBm}\n"
+                f"            Avg. power (dB_rel): {self.avg_power_dB_rel}\n"
+                f"            Avg. power (dB_abs): {self.avg_power_dB_abs}\n"
+                f"            Scintillation index: {self.scintillation_index}\n        ")
+
+
+def load(fname):
+    """Read a result saved by Fast.save (fast/fast.py:998-1002)."""
+    from astropy.io import fits
+    hdr = fits.getheader(fname)
+    data = fits.getdata(fname)
+    data /= hdr['DIFFLIM']
+    return FastResult(data, hdr['DIFFLIM'], header=hdr)

@@ -1,0 +1,213 @@
+/*
+ * fastb.h -- C ABI of libfastb.so: the B200 (sm_100a) implementation of the Monte-Carlo hot
+ * path of FAST (ojdf/fast).  Plain pointers and sizes only; no torch / C++ types.
+ *
+ * The reference is pure Python and has no FFI of its own, so each entry point below names the
+ * reference function(s) it replaces (paths relative to the reference repository); the
+ * reference-side ctypes binding a maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every `d_*` argument is a DEVICE pointer owned by the caller (e.g. a torch tensor); the
+ *     library never frees or retains it.  `stream` is a cudaStream_t passed as void* (NULL =
+ *     legacy default stream).  All work is enqueued asynchronously on that stream.
+ *   - return value 0 = success; non-zero = FASTB_ERR_*; fastb_last_error() returns a
+ *     thread-local human-readable message for the last failure on the calling thread.
+ *   - grids are row-major N x N: index r*N + c, frequency fx = (c - N/2) df, fy = (r - N/2) df
+ *     (numpy.meshgrid layout of fast/fast.py:830-833,911).
+ *   - there is no CPU fallback: every compute entry point fails with FASTB_ERR_CUDA when no
+ *     CUDA device is usable.
+ */
+#ifndef FASTB_H
+#define FASTB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FASTB_VERSION 100          /* major*10000 + minor*100 + patch */
+#define FASTB_MAX_LAYERS 32
+
+enum {
+    FASTB_OK = 0,
+    FASTB_ERR_ARG = 1,             /* invalid argument (message says which) */
+    FASTB_ERR_CUDA = 2,            /* CUDA runtime / launch failure, or no device */
+    FASTB_ERR_UNSUPPORTED = 3      /* valid request this build cannot serve (e.g. grid size) */
+};
+
+/* AO modes of ao_power_spectra.G_AO_PAOLA (fast/ao_power_spectra.py:225-270) */
+enum { FASTB_AO_NOAO = 0, FASTB_AO_AO = 1 /* 'AO' and 'TT' */, FASTB_AO_LGSAO = 2 };
+
+/* ---------------------------------------------------------------------------------------
+ * K1: residual phase PSD build.
+ * Replaces Fast.compute_powerspec (fast/fast.py:445-492) and the functions it calls:
+ *   funcs.turb_powerspectrum_vonKarman (fast/funcs.py:138-173),
+ *   ao_power_spectra.mask_lf zonal branch (fast/ao_power_spectra.py:119-141),
+ *   ao_power_spectra.G_AO_PAOLA (:225-270), Jol_alias_openloop (:163-223),
+ *   Jol_noise_openloop (:148-161), logamp_powerspec (:272-301),
+ *   and the frequency grids of SpatialFrequencies.make_main_freqs (fast/fast.py:830-833).
+ * All arithmetic is float64, evaluated in the reference's operation order.
+ * ------------------------------------------------------------------------------------- */
+typedef struct FastbPsdParams {
+    int32_t n;                      /* grid size N (even, >= 4) */
+    int32_t n_layers;               /* L, 1..FASTB_MAX_LAYERS */
+    int32_t ao_mode;                /* FASTB_AO_* */
+    int32_t alias;                  /* 1: include WFS aliasing (ignored for NOAO) */
+    int32_t lmax, kmax;             /* alias replicas, reference uses 5, 5 (fast/fast.py:462) */
+    int32_t reserved0, reserved1;
+    double df;                      /* 2 pi / (N dx)  [rad/m] */
+    double k;                       /* 2 pi / wavelength */
+    double wvl;                     /* wavelength [m] */
+    double L0, l0;                  /* outer (may be +inf) / inner scale [m] */
+    double dsubap;                  /* WFS sub-aperture pitch [m] */
+    double tloop, texp;             /* loop delay, WFS exposure [s] */
+    double noise_var;               /* NOISE (<= 0: no noise term) */
+    double dtheta[2];               /* point-ahead (x, y) [arcsec] */
+    double h[FASTB_MAX_LAYERS];     /* zenith-corrected layer heights (fast/fast.py:234) */
+    double cn2[FASTB_MAX_LAYERS];   /* zenith-corrected Cn2 dh (fast/fast.py:235) */
+    double vx[FASTB_MAX_LAYERS];    /* wind_vector[:,0] (fast/fast.py:253-257) */
+    double vy[FASTB_MAX_LAYERS];    /* wind_vector[:,1] */
+} FastbPsdParams;
+
+/* Optional per-pixel inputs (NULL = not used). */
+typedef struct FastbPsdInputs {
+    const double* d_lf_mask;        /* N*N low-frequency (corrected-region) mask; NULL = zonal
+                                       box |fx|,|fy| <= pi/dsubap computed on device.  Modal /
+                                       TT masks (Bessel based) are supplied by the host. */
+    const double* d_zfilter;        /* N*N Zernike(1..4) squared filter, required for LGSAO */
+    const double* d_pupil_filter;   /* N*N |FT(P M)|^2 / (sum P M)^2, required for d_logamp */
+} FastbPsdInputs;
+
+/* Outputs; any pointer may be NULL except d_powerspec. */
+typedef struct FastbPsdOutputs {
+    double* d_powerspec;            /* N*N    sum_l powerspec_per_layer        (fast.py:481) */
+    double* d_powerspec_per_layer;  /* L*N*N  2 pi k^2 (turb G + alias) + noise/L   (:478) */
+    double* d_turb;                 /* L*N*N  von Karman per layer                   (:448) */
+    double* d_g_ao;                 /* L*N*N  aniso-servo transfer function          (:451) */
+    double* d_alias;                /* L*N*N  aliasing PSD per layer                 (:460) */
+    double* d_noise;                /* N*N    WFS noise PSD                          (:471) */
+    double* d_logamp;               /* N*N    aperture-filtered log-amplitude PSD    (:490) */
+    double* d_integrands;           /* 3*N*N  [sum_l(G turb) M 2pi k^2, sum_l alias 2pi k^2,
+                                               W (1-M)]: integrands of aniso_servo_error,
+                                               alias_error, fitting_error (:456,464,483) */
+    float*  d_weight;               /* N*N    (-1)^(r+c) sqrt(W) df : screen-synthesis weight,
+                                               the input of fastb_screen_detect */
+    float*  d_weight_per_layer;     /* L*N*N  same per layer (TEMPORAL mode, fast.py:611-612) */
+} FastbPsdOutputs;
+
+int fastb_psd_build(const FastbPsdParams* p, const FastbPsdInputs* in,
+                    const FastbPsdOutputs* out, void* stream);
+
+/* d_weight[r*N+c] = (-1)^(r+c) * sqrt(d_W[r*N+c]) * df, for `batch` stacked N x N spectra.
+ * Replaces `rand *= numpy.sqrt(self.powerspec)` + `rand * df` (fast/fast.py:594,
+ * fast/funcs.py:218) for callers that bring their own PSD. */
+int fastb_make_weight(const double* d_W, int32_t n, int32_t batch, double df, float* d_weight,
+                      void* stream);
+
+/* out[b] = w^T P_b w for b < batch: scipy.integrate.simpson twice (fast/funcs.py:100-115),
+ * with the 1-D weight vector w (length n) supplied by the host so that the end correction
+ * follows the installed scipy. */
+int fastb_simpson2d(const double* d_P, int32_t n, int32_t batch, const double* d_w,
+                    double* d_out, void* stream);
+
+/* d_pf = |centred DFT2(d_pm)|^2 / (sum d_pm)^2 on the full N x N grid, float64, any N.
+ * Replaces funcs.pupil_filter(spline=False) (fast/funcs.py:308-315 with aotools.ft2). */
+int fastb_pupil_filter(const double* d_pm, int32_t n, double* d_pf, void* d_workspace,
+                       int64_t workspace_bytes, void* stream);
+int64_t fastb_pupil_filter_workspace_bytes(int32_t n);
+
+/* ---------------------------------------------------------------------------------------
+ * K2: phase-screen generation fused with the detector.
+ * Replaces, per complex transform ("pair" = two realisations, fast/funcs.py:220-221):
+ *   funcs.generate_random_coefficients (fast/funcs.py:352-356)      [device RNG mode]
+ *   Fast.compute_phs (fast/fast.py:589-596) incl. funcs.make_phase_fft (fast/funcs.py:210-223)
+ *   Fast.compute_logamp (fast/fast.py:639-645)                      [device RNG mode]
+ *   Fast.compute_detector (fast/fast.py:647-668)
+ * Per pair g: S = noise * |weight|, Phi = centred inverse DFT2 (N^2-scaled) of S restricted
+ * to rows/cols [lo, lo+n_pup); phi_a = Re Phi, phi_b = Im Phi;
+ *   z = exp(chi) * sum(U exp(i phi)) / sum(U);  result = |z|^2, or z when coherent.
+ * Only the per-realisation scalars are written to HBM.
+ *
+ * Realisation numbering (Fast.run layout, fast/fast.py:117-134): pair g belongs to chunk
+ * g / pairs_per_chunk; its Re realisation has global index
+ *   i_a = (g / ppc) * 2 ppc + g % ppc   and the Im realisation  i_b = i_a + ppc.
+ * chi is indexed by that global index.
+ *
+ * Device RNG (d_noise == NULL): Philox4x32-10, key = (seed lo, seed hi).  Noise cell call
+ * q = r*(N/2) + j (j < N/2) uses counter (q, g lo, g hi, 0x5CE7E000) and yields cells (r, j)
+ * from words (0,1) and (r, j+N/2) from words (2,3) by Box-Muller:
+ *   radius = sqrt(-2 ln(1 - (w_even >> 9) 2^-23)),  angle = 2 pi (w_odd >> 9) 2^-23,
+ *   Re = radius cos(angle), Im = radius sin(angle).
+ * chi_i = sigma_chi * n_i, n_i = normal (i % 4) of call i / 4 with counter
+ * (i/4 lo, i/4 hi, 0, 0x10CA3900).  Results depend only on (seed, g), never on the launch
+ * geometry or the number of GPUs.
+ * ------------------------------------------------------------------------------------- */
+enum {
+    FASTB_ALGO_AUTO = 0,
+    FASTB_ALGO_DIRECT = 1,          /* pruned direct DFT, any even N */
+    FASTB_ALGO_RADIX = 2            /* register radix-16 FFT, N = 64..2048 power of two */
+};
+
+typedef struct FastbRunParams {
+    int32_t n;                      /* N */
+    int32_t n_pup;                  /* Npxls_pup (fast/fast.py:211) */
+    int32_t lo;                     /* (N - n_pup) / 2 (fast/fast.py:390) */
+    int32_t coherent;               /* 0: |z|^2 -> 1 float; 1: z -> 2 floats (re, im) */
+    int32_t algo;                   /* FASTB_ALGO_* */
+    int32_t reserved;
+    int64_t n_pairs;                /* pairs in this call */
+    int64_t first_pair;             /* global index g of the first pair */
+    int64_t pairs_per_chunk;        /* NITER/NCHUNKS/2; > 0 */
+    uint64_t seed;
+    double u_sum;                   /* sum(U) over the n_pup x n_pup crop */
+    float sigma_chi;                /* sqrt(logamp_var); used when d_chi == NULL */
+    float reserved_f;
+} FastbRunParams;
+
+int64_t fastb_screen_detect_workspace_bytes(const FastbRunParams* p);
+
+/* d_weight  N*N floats from fastb_psd_build / fastb_make_weight
+ * d_U       n_pup*n_pup floats, pupil * pupil_mode crop (fast/fast.py:649)
+ * d_chi     NULL (device RNG) or log-amplitudes indexed by GLOBAL realisation index
+ * d_noise   NULL (device RNG) or n_pairs*N*N complex64 (re, im interleaved) unit normals,
+ *           pair-major: the reference's `rand` array (fast/fast.py:593) cast to complex64
+ * d_out_a   results of the Re realisations, element (g - first_pair) [x2 floats if coherent]
+ * d_out_b   results of the Im realisations, same indexing
+ */
+int fastb_screen_detect(const FastbRunParams* p, const float* d_weight, const float* d_U,
+                        const float* d_chi, const float* d_noise, float* d_out_a,
+                        float* d_out_b, void* d_workspace, int64_t workspace_bytes,
+                        void* stream);
+
+/* Debug / verification aid: materialise the device-RNG noise tile of pair g (N*N complex64)
+ * and the chi normals of realisations [first, first+count).  Either output may be NULL. */
+int fastb_rng_dump(uint64_t seed, int64_t pair, int32_t n, float* d_noise_tile,
+                   int64_t chi_first, int64_t chi_count, float* d_chi_normals, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K3: result statistics for the multi-GPU reduction (no reference equivalent; feeds the
+ * FastResult summaries of fast/fast.py:949-994 without a full gather).
+ * d_sums[8]   += { n, sum r, sum r^2, sum dB, sum dB^2, 0, 0, 0 }   (dB = 10 log10 r)
+ * d_minmax[2]  = { min(old, min r), max(old, max r) }
+ * d_hist[nbins+2] += histogram of dB on [db_lo, db_hi) with under/overflow in the last two.
+ * Buffers are accumulated into (caller zeroes / initialises them), so that a sum all-reduce
+ * of d_sums / d_hist and a min/max all-reduce of d_minmax combine ranks.
+ * ------------------------------------------------------------------------------------- */
+int fastb_stats(const float* d_r, int64_t n, double db_lo, double db_hi, int32_t nbins,
+                double* d_sums, double* d_minmax, unsigned long long* d_hist, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * library
+ * ------------------------------------------------------------------------------------- */
+int fastb_version(void);
+const char* fastb_last_error(void);
+int fastb_device_count(void);       /* number of usable CUDA devices, 0 if none */
+/* Kernels launched by this library on the calling thread since the last reset. */
+int64_t fastb_launch_count(void);
+void fastb_reset_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FASTB_H */

@@ -588,13 +588,13 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
 
 
 def u32_to_unit_open(u):
-    """(0, 1]: ((u >> 9) + 1) * 2^-23  -- exactly representable in fp32."""
-    return ((np.asarray(u, dtype=np.uint32) >> np.uint32(9)).astype(np.float64) + 1.0) * 2.0 ** -23
+    """(0, 1]: 1 - (u >> 9) * 2^-23 -- exactly representable in fp32 (radius argument)."""
+    return 1.0 - (np.asarray(u, dtype=np.uint32) >> np.uint32(9)).astype(np.float64) * 2.0 ** -23
 
 
 def u32_to_unit(u):
-    """[0, 1): (u >> 8) * 2^-24."""
-    return (np.asarray(u, dtype=np.uint32) >> np.uint32(8)).astype(np.float64) * 2.0 ** -24
+    """[0, 1): (u >> 9) * 2^-23 (angle fraction)."""
+    return (np.asarray(u, dtype=np.uint32) >> np.uint32(9)).astype(np.float64) * 2.0 ** -23
 
 
 def box_muller(ua, ub):

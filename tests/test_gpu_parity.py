@@ -1,0 +1,190 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via fast_b200.Fast) against the CPU oracle
+and against outputs of the unmodified reference (tests/golden).  Run with -m gpu on a B200.
+
+Tolerances: PSD terms are float64 on the device -> 1e-9 relative (of the array maximum);
+per-realisation results are float32 on the device -> 1e-4 relative (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import fast_oracle as fo
+
+pytestmark = pytest.mark.gpu
+
+MINI = ['mini_ao', 'mini_noise_L0', 'mini_noao', 'mini_tt', 'mini_modal', 'mini_lgsao',
+        'mini_axicon', 'mini_coherent', 'mini_up_w0']
+SCALARS = ['W0', 'W0_sat', 'dx', 'L', 'paa', 'r0', 'theta0', 'tau0', 'r0_los', 'theta0_los',
+           'tau0_los', 'k', 'diffraction_limit', 'aniso_servo_error', 'alias_error',
+           'noise_error', 'fitting_error', 'phs_var', 'logamp_var']
+RTOL_R = 1e-4          # per-realisation power, fp32 device arithmetic (north_star)
+
+
+def rel(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    scale = np.max(np.abs(b))
+    return 0.0 if scale == 0 else float(np.max(np.abs(a - b)) / scale)
+
+
+def worst_rel_per_item(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return float(np.max(np.abs(a - b) / np.abs(b)))
+
+
+@pytest.fixture(scope='module')
+def fast():
+    import fast_b200
+    return fast_b200
+
+
+def check_scalars(sim, g):
+    assert sim.Npxls == int(g['Npxls']) and sim.Npxls_pup == int(g['Npxls_pup'])
+    for s in SCALARS:
+        assert float(getattr(sim, s)) == pytest.approx(float(g[s]), rel=1e-9, abs=1e-300), s
+    np.testing.assert_allclose(sim.phs_var_weights, g['phs_var_weights'], rtol=1e-9)
+    np.testing.assert_allclose(list(sim.link_budget.values()), g['link_budget_vals'], rtol=1e-11)
+    np.testing.assert_allclose(sim.pupil, g['pupil'], rtol=1e-13)
+    np.testing.assert_allclose(sim.pupil_mode, g['pupil_mode'], rtol=1e-9)
+
+
+@pytest.mark.parametrize('name', MINI)
+def test_psd_every_term_vs_reference(fast, name):
+    g, p = load_golden(name)
+    sim = fast.Fast(dict(p, RNG='numpy'))
+    check_scalars(sim, g)
+    for attr in ['turb_powerspec', 'G_ao', 'alias_powerspec', 'noise_powerspec',
+                 'powerspec_per_layer', 'powerspec', 'logamp_powerspec', 'pupil_filter']:
+        want = g[attr]
+        got = np.broadcast_to(np.asarray(getattr(sim, attr), dtype=float), want.shape)
+        assert rel(got, want) < 1e-9, attr
+    assert rel(np.asarray(sim.lf_mask, dtype=float), g['lf_mask']) < 1e-12
+
+
+@pytest.mark.parametrize('name', MINI + ['c1prime', 'c3_el10', 'c3_el45', 'c3_el85', 'c4', 'c5'])
+def test_run_with_reference_noise_matches_reference(fast, name):
+    """RNG='numpy' replays the reference's own noise stream: per-realisation results must
+    match the reference run within 1e-4 relative."""
+    g, p = load_golden(name)
+    sim = fast.Fast(dict(p, RNG='numpy'))
+    check_scalars(sim, g)
+    res = sim.run()
+    want = g['r']
+    assert res._r.shape == want.shape
+    if np.iscomplexobj(want):
+        assert res._r.dtype == complex
+        assert np.max(np.abs(res._r - want) / np.abs(want)) < RTOL_R
+    else:
+        assert worst_rel_per_item(res._r, want) < RTOL_R
+    np.testing.assert_allclose(sim.logamp, g['logamp'], rtol=1e-12)
+    assert np.isfinite(sim.I).all()
+
+
+def test_c2_4000_realisations_match_reference(fast):
+    g, p = load_golden('c2')
+    sim = fast.Fast(dict(p, RNG='numpy'))
+    check_scalars(sim, g)
+    assert rel(sim.powerspec, g['powerspec']) < 1e-9
+    assert rel(sim.logamp_powerspec, g['logamp_powerspec']) < 1e-9
+    res = sim.run()
+    assert worst_rel_per_item(res._r, g['r']) < RTOL_R
+    assert res.dB_rel.mean() == pytest.approx(-3.06228, abs=2e-5)
+    assert res.dB_rel.var() == pytest.approx(2.64810, abs=2e-4)
+
+
+@pytest.mark.parametrize('N', [64, 128, 256, 512, 1024])
+def test_device_rng_noise_matches_philox_restatement(fast, N):
+    tile, chi = fast._lib.rng_dump(seed=0x1234567890ABCDEF, pair=(1 << 33) + 5, n=N, device='cuda',
+                                   chi_first=1001, chi_count=64)
+    want = fo.device_noise_pair(0x1234567890ABCDEF, (1 << 33) + 5, N)
+    got = torch.view_as_complex(tile).cpu().numpy()
+    assert np.max(np.abs(got - want)) < 2e-5          # MUFU lg2/sin/cos vs libm
+    np.testing.assert_allclose(chi.cpu().numpy(), fo.device_chi_normals(0x1234567890ABCDEF, 1001, 64),
+                               atol=2e-5)
+
+
+@pytest.mark.parametrize('name,npairs', [('mini_ao', 10), ('mini_coherent', 10), ('c2', 3), ('c1prime', 3)])
+def test_device_rng_run_matches_oracle(fast, name, npairs):
+    """Device Philox noise, restated on the CPU, through the oracle pipeline."""
+    g, p = load_golden(name)
+    niter, nch = 4 * npairs, 2
+    sim = fast.Fast(dict(p, NITER=niter, NCHUNKS=nch, SEED=77))
+    got = sim.run()._r
+    init = fo.build(p)
+    want = fo.run_mc_device_rng(init, 77, 2 * npairs, niter // nch // 2)
+    assert np.max(np.abs(got - want) / np.abs(want)) < 5e-4   # noise itself differs by ~1e-6 (MUFU)
+
+
+@pytest.mark.parametrize('name', ['mini_ao', 'c2', 'c4', 'c5'])
+def test_radix_and_direct_paths_agree(fast, name):
+    g, p = load_golden(name)
+    sim = fast.Fast(dict(p, NITER=8, NCHUNKS=1, SEED=5))
+    a1, b1 = sim.screen_detect(3, 4, algo=fast._lib.ALGO_RADIX)
+    a2, b2 = sim.screen_detect(3, 4, algo=fast._lib.ALGO_DIRECT)
+    for x, y in ((a1, a2), (b1, b2)):
+        x, y = x.cpu().numpy(), y.cpu().numpy()
+        assert np.max(np.abs(x - y) / np.abs(y)) < 1e-4
+
+
+def test_results_do_not_depend_on_launch_split(fast):
+    """Counter-based RNG on the global pair index: any split of the pair range, hence any
+    number of GPUs, gives bit-identical per-realisation values."""
+    g, p = load_golden('mini_ao')
+    sim = fast.Fast(dict(p, NITER=64, NCHUNKS=4, SEED=9))
+    a, b = sim.screen_detect(0, 32)
+    a1, b1 = sim.screen_detect(0, 13)
+    a2, b2 = sim.screen_detect(13, 19)
+    assert torch.equal(a, torch.cat([a1, a2])) and torch.equal(b, torch.cat([b1, b2]))
+    r1, r2 = sim.run()._r, sim.run()._r
+    np.testing.assert_array_equal(r1, r2)
+
+
+def test_coherent_modulus_equals_incoherent(fast):
+    """|z|^2 of the coherent output == incoherent output for the same seed (SURVEY 8c ii)."""
+    g, p = load_golden('mini_ao')
+    r_inc = fast.Fast(dict(p, SEED=11)).run()._r
+    z = fast.Fast(dict(p, SEED=11, COHERENT=True)).run()._r
+    assert z.dtype == complex
+    np.testing.assert_allclose(np.abs(z) ** 2, r_inc, rtol=2e-6)
+
+
+def test_screen_variance_matches_psd_integral(fast):
+    """Flat unit pupil over the whole crop and chi = 0: E|z|^2 ~ exp(-var) coupling; cheaper
+    exact property: with weight scaled to 0 the detector returns exactly 1."""
+    g, p = load_golden('mini_ao')
+    sim = fast.Fast(dict(p, SEED=3))
+    sim._d['weight'].zero_()
+    a, b = sim.screen_detect(0, 4, chi=torch.zeros(sim.Niter, dtype=torch.float32, device='cuda'))
+    np.testing.assert_allclose(a.cpu().numpy(), 1.0, rtol=1e-6)
+    np.testing.assert_allclose(b.cpu().numpy(), 1.0, rtol=1e-6)
+
+
+def test_error_behaviour(fast):
+    g, p = load_golden('mini_ao')
+    with pytest.raises(Exception, match='NCHUNKS must divide NITER'):
+        fast.Fast(dict(p, NITER=10, NCHUNKS=3))
+    with pytest.raises(Exception, match='must be even'):
+        fast.Fast(dict(p, NITER=10, NCHUNKS=2))
+    with pytest.raises(Exception, match='Mode not recognised'):
+        fast.Fast(dict(p, AO_MODE='AO_PA'))
+    with pytest.raises(Exception, match='Either config file name or params dict'):
+        fast.Fast(3)
+    sim = fast.Fast(dict(p))
+    rp = sim._run_params(4, 0)
+    rp.n_pup = 1000
+    with pytest.raises(fast._lib.FastbError, match='n_pup'):
+        fast._lib.screen_detect_workspace_bytes(rp)
+
+
+def test_stats_kernel(fast):
+    g, p = load_golden('mini_ao')
+    sim = fast.Fast(dict(p, NITER=4000, NCHUNKS=2, SEED=21))
+    res = sim.run()
+    st = sim.result_stats(db_lo=-40, db_hi=5, nbins=450)
+    assert st['n'] == 4000
+    assert st['mean'] == pytest.approx(res._r.mean(), rel=1e-6)
+    assert st['scintillation_index'] == pytest.approx(res.scintillation_index, rel=1e-5)
+    assert st['mean_dB'] == pytest.approx(res.dB_rel.mean(), rel=1e-6)
+    assert st['min'] == pytest.approx(res._r.min()) and st['max'] == pytest.approx(res._r.max())
+    h, _ = np.histogram(res.dB_rel, bins=450, range=(-40, 5))
+    assert st['hist'][:450].sum() + st['hist'][450:].sum() == 4000
+    assert np.abs(st['hist'][:450] - h).sum() <= 4      # bin-edge rounding only
