@@ -57,39 +57,51 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, False, [], set(), None
+        self.note = None
 
     def run(self):
+        names = {'hw_slowdown': 0x8, 'sw_power_cap': 0x4, 'sw_thermal_slowdown': 0x20,
+                 'hw_thermal_slowdown': 0x40, 'hw_power_brake_slowdown': 0x80}
         try:
             import pynvml
             pynvml.nvmlInit()
             h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
-            names = {'hw_slowdown': 0x8, 'sw_power_cap': 0x4, 'sw_thermal_slowdown': 0x20,
-                     'hw_thermal_slowdown': 0x40, 'hw_power_brake_slowdown': 0x80}
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            get_mask = getattr(pynvml, 'nvmlDeviceGetCurrentClocksEventReasons', None) or \
+                getattr(pynvml, 'nvmlDeviceGetCurrentClocksThrottleReasons')
             while not self.stop_flag:
-                self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                self.samples.append(int(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
                 try:
-                    mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                    mask = int(get_mask(h))
+                    for k, bit in names.items():
+                        if mask & bit:
+                            self.reasons.add(k)
+                except Exception as e:
+                    self.note = f'reasons unavailable: {type(e).__name__}'
+                time.sleep(0.05)
+        except Exception as e:
+            self.note = f'pynvml failed ({type(e).__name__}: {e}); nvidia-smi polling'
+            q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+                'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+            keys = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+            while not self.stop_flag:
+                try:
+                    out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q,
+                                          '--format=csv,noheader,nounits'], capture_output=True, text=True).stdout
+                    f = [x.strip() for x in out.strip().split(',')]
+                    self.samples.append(int(f[0]))
+                    self.max_mhz = int(f[1])
+                    for k, v in zip(keys, f[2:]):
+                        if v.lower().startswith('active'):
+                            self.reasons.add(k)
                 except Exception:
-                    mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                for k, bit in names.items():
-                    if mask & bit:
-                        self.reasons.add(k)
-                time.sleep(0.1)
-        except Exception as e:   # fall back to one nvidia-smi query
-            try:
-                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=clocks.sm,clocks.max.sm',
-                                      '--format=csv,noheader,nounits'], capture_output=True, text=True).stdout
-                a, b = out.strip().split(',')
-                self.samples.append(int(a))
-                self.max_mhz = int(b)
-            except Exception:
-                self.reasons.add(f'unavailable: {type(e).__name__}')
+                    break
 
     def summary(self):
         s = sorted(self.samples)
-        return {'sm_mhz': s[len(s) // 2] if s else None, 'sm_max_mhz': self.max_mhz,
-                'reasons': sorted(self.reasons), 'samples': len(s)}
+        return {'sm_mhz': s[len(s) // 2] if s else None, 'sm_min_mhz': s[0] if s else None,
+                'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons), 'samples': len(s),
+                'note': self.note}
 
 
 # ------------------------------------------------------------------------- CPU (oracle port)

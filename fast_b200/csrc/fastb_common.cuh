@@ -53,19 +53,23 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
     return make_uint4(c0, c1, c2, c3);
 }
 
-// top 23 bits -> [0, 1) exactly, without an int->float conversion
-__device__ __forceinline__ float u23(uint32_t w) {
-    return __uint_as_float(0x3f800000u | (w >> 9)) - 1.0f;
-}
-
-// Box-Muller: radius from wa (argument in (0, 1]), angle from wb.  MUFU lg2 / sqrt / sin / cos.
-__device__ __forceinline__ float2 box_muller(uint32_t wa, uint32_t wb) {
-    const float u1 = 2.0f - __uint_as_float(0x3f800000u | (wa >> 9));     // 1 - (wa>>9) 2^-23
-    const float rad = sqrtf(-1.3862943611198906f * __log2f(u1));          // sqrt(-2 ln u1)
-    const float ang = 6.283185307179586f * u23(wb);
+// Box-Muller on two Philox words, scaled by w: radius from wa (argument 1 - (wa>>9) 2^-23 in
+// (0, 1]), angle 2 pi (wb>>9) 2^-23.  The mantissa trick builds 1+u in [1, 2) without an
+// int->float conversion; sin/cos are 2 pi-periodic so 2 pi (1+u) is used directly.
+// 4 MUFU (lg2, sqrt, sin, cos) + 5 FMUL + 1 FADD per complex sample.
+__device__ __forceinline__ float2 weighted_normal(uint32_t wa, uint32_t wb, float w) {
+    const float u1 = 2.0f - __uint_as_float(0x3f800000u | (wa >> 9));
+    float rad;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(-1.3862943611198906f * __log2f(u1)));
+    rad *= w;
+    const float ang = 6.283185307179586f * __uint_as_float(0x3f800000u | (wb >> 9));
     float s, c;
     __sincosf(ang, &s, &c);
     return make_float2(rad * c, rad * s);
+}
+
+__device__ __forceinline__ float2 box_muller(uint32_t wa, uint32_t wb) {
+    return weighted_normal(wa, wb, 1.0f);
 }
 
 // standard normal n_i used for the log-amplitude of global realisation index i

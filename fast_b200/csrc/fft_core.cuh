@@ -111,11 +111,19 @@ struct LineFFT {
     // element index held in register m of thread t before phase A
     FASTB_HD static int n_in(int t, int m) { return t + S1 * m; }
 
-    // phase A: dft16 over m, twiddle, write exchange buffer.  tw[j] = exp(+2 pi i j / N)
-    FASTB_HD static void phase_a(int t, float2 (&v)[16], const float2* tw, float2* buf) {
+    // Twiddle tables (thread-major inner index => conflict-free shared-memory reads):
+    //   twa[a * S1 + t]  = exp(+2 pi i (t a) / N)          a < 16, t < S1      (N entries)
+    //   twb[a2 * S2 + t2] = exp(+2 pi i (16 t2 a2) / N)    a2 < 16, t2 < S2    (S2 > 1 only)
+    static constexpr int kTwA = N;
+    static constexpr int kTwB = (kThree && S2 > 1) ? 16 * S2 : 0;
+    FASTB_HD static int twa_exponent(int idx) { return ((idx % S1) * (idx / S1)) & (N - 1); }
+    FASTB_HD static int twb_exponent(int idx) { return (16 * (idx % S2) * (idx / S2)) & (N - 1); }
+
+    // phase A: dft16 over m, twiddle, write exchange buffer
+    FASTB_HD static void phase_a(int t, float2 (&v)[16], const float2* twa, float2* buf) {
         dft16(v);
 #pragma unroll
-        for (int a = 1; a < 16; ++a) v[a] = cmul(v[a], tw[(t * a) & (N - 1)]);
+        for (int a = 1; a < 16; ++a) v[a] = cmul(v[a], twa[a * S1 + t]);
         if (kThree) {
 #pragma unroll
             for (int a = 0; a < 16; ++a) buf[a * (S1 + kPadA) + t] = v[a];
@@ -127,14 +135,14 @@ struct LineFFT {
 
     // phase B (N >= 256): gather, dft16 over m2, twiddle.  If S2 > 1 the caller must sync
     // and then call phase_b_store before phase C.
-    FASTB_HD static void phase_b(int u, float2 (&v)[16], const float2* tw, const float2* buf) {
+    FASTB_HD static void phase_b(int u, float2 (&v)[16], const float2* twb, const float2* buf) {
         const int a = u / S2, t2 = u % S2;
 #pragma unroll
         for (int m2 = 0; m2 < 16; ++m2) v[m2] = buf[a * (S1 + kPadA) + t2 + S2 * m2];
         dft16(v);
         if (S2 > 1) {
 #pragma unroll
-            for (int a2 = 1; a2 < 16; ++a2) v[a2] = cmul(v[a2], tw[(16 * t2 * a2) & (N - 1)]);
+            for (int a2 = 1; a2 < 16; ++a2) v[a2] = cmul(v[a2], twb[a2 * S2 + t2]);
         }
     }
 

@@ -12,6 +12,8 @@
 #include "fastb_common.cuh"
 #include "fft_core.cuh"
 
+#include <stdlib.h>
+
 namespace fastb {
 namespace {
 
@@ -109,12 +111,13 @@ __device__ __forceinline__ void line_sync() {
 
 // run phases A..C of the line FFT on v (see fft_core.cuh); u = thread index within the line
 template <int LOG2N>
-__device__ __forceinline__ void line_fft(int u, float2 (&v)[16], const float2* tw, float2* buf) {
+__device__ __forceinline__ void line_fft(int u, float2 (&v)[16], const float2* twa, const float2* twb,
+                                         float2* buf) {
     using F = LineFFT<LOG2N>;
-    F::phase_a(u, v, tw, buf);
+    F::phase_a(u, v, twa, buf);
     line_sync<F::S1>();
     if (F::kThree) {
-        F::phase_b(u, v, tw, buf);
+        F::phase_b(u, v, twb, buf);
         if (F::S2 > 1) {
             line_sync<F::S1>();
             F::phase_b_store(u, v, buf);
@@ -127,90 +130,87 @@ __device__ __forceinline__ void line_fft(int u, float2 (&v)[16], const float2* t
     line_sync<F::S1>();          // buffer may be rewritten by the next line
 }
 
-template <int LOG2N, bool RNG>
-__global__ void __launch_bounds__(kThreads, 2) screen_detect_radix(const __grid_constant__ RunArgs a) {
+// One loop body serves both passes (keeps the kernel inside the instruction cache): iterations
+// [0, n1) are frequency rows (noise -> FFT -> pruned store to T[c][r']), iterations [n1, n1+n2)
+// are kept columns (load T[c][:] -> FFT -> detector accumulation).  No CTA-wide barrier inside a
+// pass when a line fits in a warp (N <= 512).
+template <int LOG2N, bool RNG, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) screen_detect_radix(const __grid_constant__ RunArgs a) {
     using F = LineFFT<LOG2N>;
     constexpr int N = F::N, S1 = F::S1, LPB = kThreads / S1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* tw = reinterpret_cast<float2*>(smem_raw);
-    float2* bufs = tw + N;
-    const int pitch = a.n_pup | 1;
-    float2* tile = bufs + LPB * F::kBuf;
-    float* red = reinterpret_cast<float*>(tile + LPB * pitch);
+    float2* twa = reinterpret_cast<float2*>(smem_raw);
+    float2* twb = twa + F::kTwA;
+    float2* bufs = twb + F::kTwB;
+    float* red = reinterpret_cast<float*>(bufs + LPB * F::kBuf);
 
     const int tid = threadIdx.x;
     const int ln = tid / S1, u = tid % S1;
     float2* buf = bufs + ln * F::kBuf;
     const int P = a.n_pup, lo = a.lo;
 
-    for (int j = tid; j < N; j += kThreads) {
+    for (int j = tid; j < F::kTwA + F::kTwB; j += kThreads) {
+        const int ex = j < F::kTwA ? F::twa_exponent(j) : F::twb_exponent(j - F::kTwA);
         double s, c;
-        sincospi(2.0 * (double)j / (double)N, &s, &c);
-        tw[j] = make_float2((float)c, (float)s);
+        sincospi(2.0 * (double)ex / (double)N, &s, &c);
+        twa[j] = make_float2((float)c, (float)s);
     }
     __syncthreads();
 
     float2* T = a.scratch + (size_t)blockIdx.x * N * P;
     const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
+    const int n1 = N / LPB, n2 = (P + LPB - 1) / LPB;
 
     for (long long pair = blockIdx.x; pair < a.n_pairs; pair += gridDim.x) {
         const unsigned long long g = (unsigned long long)(a.first_pair + pair);
-        // ---------------- pass 1: rows ----------------
-        for (int row0 = 0; row0 < N; row0 += LPB) {
-            const int r = row0 + ln;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int it = 0; it < n1 + n2; ++it) {
+            const bool rows = it < n1;
+            if (it == n1) __syncthreads();            // every row of T is stored before a column is read
+            const int line = (rows ? it : it - n1) * LPB + ln;      // r' (pass 1) or c (pass 2)
             float2 v[16];
-            const float* wrow = a.weight + (size_t)r * N;
-            if (RNG) {
+            if (rows) {
+                const float* wrow = a.weight + (size_t)line * N;
+                if (RNG) {
 #pragma unroll
-                for (int m = 0; m < 8; ++m) {
-                    const int j = u + S1 * m;
-                    const uint4 w = philox4x32_10((uint32_t)(r * (N / 2) + j), (uint32_t)g,
-                                                  (uint32_t)(g >> 32), kStreamNoise, k0, k1);
-                    const float2 n0 = box_muller(w.x, w.y), n1 = box_muller(w.z, w.w);
-                    const float w0 = __ldg(wrow + j), w1 = __ldg(wrow + j + N / 2);
-                    v[m] = make_float2(n0.x * w0, n0.y * w0);
-                    v[m + 8] = make_float2(n1.x * w1, n1.y * w1);
+                    for (int m = 0; m < 8; ++m) {
+                        const int j = u + S1 * m;
+                        const uint4 w = philox4x32_10((uint32_t)(line * (N / 2) + j), (uint32_t)g,
+                                                      (uint32_t)(g >> 32), kStreamNoise, k0, k1);
+                        v[m] = weighted_normal(w.x, w.y, __ldg(wrow + j));
+                        v[m + 8] = weighted_normal(w.z, w.w, __ldg(wrow + j + N / 2));
+                    }
+                } else {
+                    const float2* nrow = a.noise + ((size_t)pair * N + line) * N;
+#pragma unroll
+                    for (int m = 0; m < 16; ++m) {
+                        const int j = u + S1 * m;
+                        const float2 nz = __ldg(nrow + j);
+                        const float w0 = __ldg(wrow + j);
+                        v[m] = make_float2(nz.x * w0, nz.y * w0);
+                    }
                 }
             } else {
-                const float2* nrow = a.noise + ((size_t)pair * N + r) * N;
+                const float2* tcol = T + (size_t)(line < P ? line : 0) * N;
 #pragma unroll
-                for (int m = 0; m < 16; ++m) {
-                    const int j = u + S1 * m;
-                    const float2 nz = __ldg(nrow + j);
-                    const float w0 = __ldg(wrow + j);
-                    v[m] = make_float2(nz.x * w0, nz.y * w0);
+                for (int m = 0; m < 16; ++m) v[m] = __ldcg(tcol + u + S1 * m);
+            }
+            line_fft<LOG2N>(u, v, twa, twb, buf);
+            if (rows) {
+                float2* trow = T + line;                      // T[c * N + r']
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    const unsigned c = (unsigned)(F::k_out(u, e) - lo);
+                    if (c < (unsigned)P) __stcg(trow + (size_t)c * N, v[e]);
                 }
-            }
-            line_fft<LOG2N>(u, v, tw, buf);
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-                const int c = F::k_out(u, e) - lo;
-                if (c >= 0 && c < P) tile[ln * pitch + c] = v[e];
-            }
-            __syncthreads();
-            for (int idx = tid; idx < P * LPB; idx += kThreads) {
-                const int c = idx / LPB, l2 = idx % LPB;
-                __stcg(&T[(size_t)c * N + row0 + l2], tile[l2 * pitch + c]);
-            }
-            __syncthreads();
-        }
-        // ---------------- pass 2: columns + detector ----------------
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int col0 = 0; col0 < P; col0 += LPB) {
-            const int c = col0 + ln;
-            const bool active = c < P;
-            float2 v[16];
-            const float2* tcol = T + (size_t)(active ? c : 0) * N;
-#pragma unroll
-            for (int m = 0; m < 16; ++m) v[m] = __ldcg(tcol + u + S1 * m);
-            line_fft<LOG2N>(u, v, tw, buf);
-            if (active) {
-                const float* ucol = a.u_t + (size_t)c * P;
+            } else if (line < P) {
+                const float* ucol = a.u_t + (size_t)line * P;
+                const int par = (line + lo) & 1;
 #pragma unroll
                 for (int e = 0; e < 16; ++e) {
                     const int k = F::k_out(u, e);
-                    const int rr = k - lo;
-                    if (rr >= 0 && rr < P) accumulate(v[e], __ldg(ucol + rr), ((k + c + lo) & 1) != 0, acc);
+                    const unsigned rr = (unsigned)(k - lo);
+                    if (rr < (unsigned)P) accumulate(v[e], __ldg(ucol + rr), ((k & 1) ^ par) != 0, acc);
                 }
             }
         }
@@ -323,10 +323,10 @@ __global__ void rng_dump_kernel(unsigned long long seed, unsigned long long g, i
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 template <int LOG2N>
-size_t radix_smem_bytes(int n_pup) {
+size_t radix_smem_bytes() {
     using F = LineFFT<LOG2N>;
     const int LPB = kThreads / F::S1;
-    return sizeof(float2) * ((size_t)F::N + (size_t)LPB * F::kBuf + (size_t)LPB * (n_pup | 1)) +
+    return sizeof(float2) * ((size_t)F::kTwA + F::kTwB + (size_t)LPB * F::kBuf) +
            sizeof(float) * 4 * (kThreads / 32);
 }
 
@@ -349,11 +349,15 @@ int sm_count(int* out) {
 
 constexpr int kMaxCtasPerSm = 4;
 
-template <int LOG2N>
-int launch_radix(const RunArgs& args, bool rng, int max_grid, cudaStream_t st) {
-    const size_t smem = radix_smem_bytes<LOG2N>(args.n_pup);
-    auto kern = rng ? screen_detect_radix<LOG2N, true> : screen_detect_radix<LOG2N, false>;
+int g_min_blocks = 0;      // 0 = default; FASTB_MIN_BLOCKS env (2 or 3) selects the register budget
+
+template <int LOG2N, int MINB>
+int launch_radix_mb(const RunArgs& args, bool rng, int max_grid, cudaStream_t st) {
+    const size_t smem = radix_smem_bytes<LOG2N>();
+    auto kern = rng ? screen_detect_radix<LOG2N, true, MINB> : screen_detect_radix<LOG2N, false, MINB>;
     FASTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FASTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                    cudaSharedmemCarveoutMaxShared));
     int per_sm = 0, sms = 0;
     FASTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
     if (per_sm < 1) {
@@ -368,6 +372,18 @@ int launch_radix(const RunArgs& args, bool rng, int max_grid, cudaStream_t st) {
     if (grid > max_grid) grid = max_grid;
     kern<<<(unsigned)grid, kThreads, smem, st>>>(args);
     return check_launch("screen_detect_radix");
+}
+
+template <int LOG2N>
+int launch_radix(const RunArgs& args, bool rng, int max_grid, cudaStream_t st) {
+    if (g_min_blocks == 0) {
+        const char* e = getenv("FASTB_MIN_BLOCKS");
+        const int v = e ? atoi(e) : 3;
+        g_min_blocks = (v == 2 || v == 4) ? v : 3;
+    }
+    if (g_min_blocks == 2) return launch_radix_mb<LOG2N, 2>(args, rng, max_grid, st);
+    if (g_min_blocks == 4) return launch_radix_mb<LOG2N, 4>(args, rng, max_grid, st);
+    return launch_radix_mb<LOG2N, 3>(args, rng, max_grid, st);
 }
 
 }  // namespace

@@ -14,22 +14,29 @@ template <int LOG2N>
 double run_one(unsigned seed) {
     using F = LineFFT<LOG2N>;
     constexpr int N = F::N;
-    std::vector<float2> x(N), tw(N), buf(F::kBuf), X(N);
+    std::vector<float2> x(N), twa(F::kTwA), twb(F::kTwB + 1), buf(F::kBuf), X(N);
     std::vector<int> seen(N, 0);
     srand(seed);
     for (int i = 0; i < N; ++i) {
         x[i] = make_float2((float)rand() / RAND_MAX - 0.5f, (float)rand() / RAND_MAX - 0.5f);
-        tw[i] = make_float2((float)cos(2.0 * M_PI * i / N), (float)sin(2.0 * M_PI * i / N));
+    }
+    for (int i = 0; i < F::kTwA; ++i) {
+        const int ex = F::twa_exponent(i);
+        twa[i] = make_float2((float)cos(2.0 * M_PI * ex / N), (float)sin(2.0 * M_PI * ex / N));
+    }
+    for (int i = 0; i < F::kTwB; ++i) {
+        const int ex = F::twb_exponent(i);
+        twb[i] = make_float2((float)cos(2.0 * M_PI * ex / N), (float)sin(2.0 * M_PI * ex / N));
     }
     float2 v[16];
     for (int t = 0; t < F::S1; ++t) {
         for (int m = 0; m < 16; ++m) v[m] = x[F::n_in(t, m)];
-        F::phase_a(t, v, tw.data(), buf.data());
+        F::phase_a(t, v, twa.data(), buf.data());
     }
     if (F::kThree) {
         std::vector<float2> keep(16 * F::S1);
         for (int u = 0; u < F::S1; ++u) {
-            F::phase_b(u, v, tw.data(), buf.data());
+            F::phase_b(u, v, twb.data(), buf.data());
             for (int e = 0; e < 16; ++e) keep[u * 16 + e] = v[e];
         }
         if (F::S2 > 1) {

@@ -97,9 +97,12 @@ def test_device_rng_noise_matches_philox_restatement(fast, N):
                                    chi_first=1001, chi_count=64)
     want = fo.device_noise_pair(0x1234567890ABCDEF, (1 << 33) + 5, N)
     got = torch.view_as_complex(tile).cpu().numpy()
-    assert np.max(np.abs(got - want)) < 2e-5          # MUFU lg2/sin/cos vs libm
+    # MUFU lg2 has 2^-22 ABSOLUTE error near 1, so the rare tiny-radius samples differ by up to
+    # ~1e-4; everything else agrees to ~1e-6
+    err = np.abs(got - want)
+    assert err.max() < 3e-4 and np.sqrt((err ** 2).mean()) < 2e-6
     np.testing.assert_allclose(chi.cpu().numpy(), fo.device_chi_normals(0x1234567890ABCDEF, 1001, 64),
-                               atol=2e-5)
+                               atol=3e-4)
 
 
 @pytest.mark.parametrize('name,npairs', [('mini_ao', 10), ('mini_coherent', 10), ('c2', 3), ('c1prime', 3)])
