@@ -121,9 +121,11 @@ def _cpu_worker_init(workload, seed_base):
 def _cpu_worker_step(n_real):
     """n_real realisations in chunks of <= 50 pairs, exactly the reference's chunk loop."""
     fo, init, rng = _W['fo'], _W['init'], _W['rng']
+    # chunk so that one process holds ~32 MiB of complex128 noise (the reference's NCHUNKS knob)
+    chunk = max(2, 2 * ((1 << 21) // (init['N'] * init['N'])))
     done = 0
     while done < n_real:
-        m = min(100, n_real - done)
+        m = min(chunk, n_real - done)
         fo.run_mc(init, rng, niter=m, nchunks=1)
         done += m
     return done
@@ -148,7 +150,7 @@ def run_reference(args):
     if rank != 0:
         return
     factory, n_real, desc = WORKLOADS[args.workload]
-    cores = os.cpu_count() or 1
+    cores = min(os.cpu_count() or 1, 128)
     rate_guess = {'c2': 200.0, 'c4': 45.0, 'c5': 10.0}[args.workload]
     budget = 150.0 / max(1, args.steps + args.warmup)              # seconds per step
     per_proc = max(2, int(budget * rate_guess * 0.6) // 2 * 2)

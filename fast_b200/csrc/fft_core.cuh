@@ -177,15 +177,21 @@ struct LineFFT {
         }
     }
 
-    // output index k held in register e of thread u after the last phase
-    FASTB_HD static int k_out(int u, int e) {
-        if (kThree) {
-            if (S2 == 1) return u + 16 * e;
-            const int a = u / S2, j = u % S2, i = e / S2, b2 = e % S2;
-            return a + 16 * (i * S2 + j) + 256 * b2;
-        }
-        const int j = u % SF, i = e / SF, b = e % SF;
-        return (i * SF + j) + 16 * b;
+    // Output index k held in register e of thread u after the last phase, split into a
+    // per-thread base and a compile-time offset: k = k_base(u) + k_off(e).  Offsets are even.
+    FASTB_HD static int k_base(int u) {
+        if (kThree) return (S2 == 1) ? u : (u / S2) + 16 * (u % S2);
+        return u % SF;
+    }
+    FASTB_HD static constexpr int k_off(int e) {
+        return kThree ? ((S2 == 1) ? 16 * e : 16 * S2 * (e / S2) + 256 * (e % S2))
+                      : SF * (e / SF) + 16 * (e % SF);
+    }
+    FASTB_HD static int k_out(int u, int e) { return k_base(u) + k_off(e); }
+    FASTB_HD static constexpr bool k_off_all_even() {
+        for (int e = 0; e < 16; ++e)
+            if (k_off(e) & 1) return false;
+        return true;
     }
 };
 

@@ -34,27 +34,18 @@ struct RunArgs {
     int rows_per_block;       // direct kernel only
 };
 
-__device__ __forceinline__ void fast_sincos(float x, float* s, float* c) {
-    const float k = rintf(x * 0.15915494309189535f);
-    float r = fmaf(-k, 6.2831854820251465f, x);
-    r = fmaf(-k, -1.7484556000744883e-07f, r);
-    *s = __sinf(r);
-    *c = __cosf(r);
-}
-
-// accumulate U exp(i phi) for the two screens carried by one complex sample
-__device__ __forceinline__ void accumulate(float2 phi, float u, bool negate, float (&acc)[4]) {
-    if (negate) {
-        phi.x = -phi.x;
-        phi.y = -phi.y;
-    }
+// accumulate U exp(i s phi) for the two screens carried by one complex sample; us = s * u with
+// s = +-1 the output sign of the centred transform (cos is even, so only the sine terms see it).
+// sin.approx / cos.approx reduce the argument internally (x / 2pi in fp32): for |phi| < ~30 rad
+// the phase error stays ~1e-6 rad, far below the 1e-4 parity budget on the power.
+__device__ __forceinline__ void accumulate(float2 phi, float u, float us, float (&acc)[4]) {
     float s, c;
-    fast_sincos(phi.x, &s, &c);
+    __sincosf(phi.x, &s, &c);
     acc[0] = fmaf(u, c, acc[0]);
-    acc[1] = fmaf(u, s, acc[1]);
-    fast_sincos(phi.y, &s, &c);
+    acc[1] = fmaf(us, s, acc[1]);
+    __sincosf(phi.y, &s, &c);
     acc[2] = fmaf(u, c, acc[2]);
-    acc[3] = fmaf(u, s, acc[3]);
+    acc[3] = fmaf(us, s, acc[3]);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -161,6 +152,15 @@ __global__ void __launch_bounds__(kThreads, MINB) screen_detect_radix(const __gr
     const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
     const int n1 = N / LPB, n2 = (P + LPB - 1) / LPB;
 
+    static_assert(F::k_off_all_even(), "the output sign is taken per thread: k_off must be even");
+    // which of this thread's 16 outputs fall inside the crop [lo, lo+P): the same for every
+    // line of both passes, so it is computed once and tested bit by bit
+    const int kb = F::k_base(u) - lo;
+    unsigned need = 0;
+#pragma unroll
+    for (int e = 0; e < 16; ++e)
+        if ((unsigned)(kb + F::k_off(e)) < (unsigned)P) need |= 1u << e;
+
     for (long long pair = blockIdx.x; pair < a.n_pairs; pair += gridDim.x) {
         const unsigned long long g = (unsigned long long)(a.first_pair + pair);
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -197,20 +197,20 @@ __global__ void __launch_bounds__(kThreads, MINB) screen_detect_radix(const __gr
             }
             line_fft<LOG2N>(u, v, twa, twb, buf);
             if (rows) {
-                float2* trow = T + line;                      // T[c * N + r']
+                float2* tb = T + ((long long)kb * N + line);  // &T[(k - lo) * N + r'] at k_off = 0
 #pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    const unsigned c = (unsigned)(F::k_out(u, e) - lo);
-                    if (c < (unsigned)P) __stcg(trow + (size_t)c * N, v[e]);
-                }
+                for (int e = 0; e < 16; ++e)
+                    if (need & (1u << e)) __stcg(tb + (long long)F::k_off(e) * N, v[e]);
             } else if (line < P) {
-                const float* ucol = a.u_t + (size_t)line * P;
-                const int par = (line + lo) & 1;
+                const float* ub = a.u_t + ((long long)line * P + kb);
+                // output sign (-1)^(r + c): k_off is even, so it is one value per thread and line
+                const float sgn = ((F::k_base(u) + line + lo) & 1) ? -1.f : 1.f;
 #pragma unroll
                 for (int e = 0; e < 16; ++e) {
-                    const int k = F::k_out(u, e);
-                    const unsigned rr = (unsigned)(k - lo);
-                    if (rr < (unsigned)P) accumulate(v[e], __ldg(ucol + rr), ((k & 1) ^ par) != 0, acc);
+                    if (need & (1u << e)) {
+                        const float uu = __ldg(ub + F::k_off(e));
+                        accumulate(v[e], uu, uu * sgn, acc);
+                    }
                 }
             }
         }
@@ -293,7 +293,8 @@ __global__ void __launch_bounds__(kThreads) screen_detect_direct(const __grid_co
                 ti += kk;
                 if (ti >= N) ti -= N;
             }
-            accumulate(make_float2(sr, si), a.u_t[(size_t)c * P + rr], ((kk + c + lo) & 1) != 0, acc);
+            const float uu = a.u_t[(size_t)c * P + rr];
+            accumulate(make_float2(sr, si), uu, ((kk + c + lo) & 1) ? -uu : uu, acc);
         }
         finish_pair(a, pair, acc, red);
     }
@@ -378,12 +379,15 @@ template <int LOG2N>
 int launch_radix(const RunArgs& args, bool rng, int max_grid, cudaStream_t st) {
     if (g_min_blocks == 0) {
         const char* e = getenv("FASTB_MIN_BLOCKS");
-        const int v = e ? atoi(e) : 3;
-        g_min_blocks = (v == 2 || v == 4) ? v : 3;
+        const int v = e ? atoi(e) : -1;
+        g_min_blocks = (v >= 2 && v <= 4) ? v : -1;
     }
-    if (g_min_blocks == 2) return launch_radix_mb<LOG2N, 2>(args, rng, max_grid, st);
-    if (g_min_blocks == 4) return launch_radix_mb<LOG2N, 4>(args, rng, max_grid, st);
-    return launch_radix_mb<LOG2N, 3>(args, rng, max_grid, st);
+    // measured on B200 (profiles/): 3 CTAs/SM (<= 80 registers, no spills) is best except at
+    // N = 512, where 2 CTAs/SM with 124 registers wins
+    const int mb = g_min_blocks > 0 ? g_min_blocks : (LOG2N == 9 ? 2 : 3);
+    if (mb == 2) return launch_radix_mb<LOG2N, 2>(args, rng, max_grid, st);
+    if (mb == 3) return launch_radix_mb<LOG2N, 3>(args, rng, max_grid, st);
+    return launch_radix_mb<LOG2N, 4>(args, rng, max_grid, st);
 }
 
 }  // namespace

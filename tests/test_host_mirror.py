@@ -1,0 +1,97 @@
+"""CPU tests of the host-side mirror of the reference interface (no GPU): config handling,
+profile generators, pupil / mode construction and geometry helpers against the golden outputs
+of the unmodified reference, and agreement of the two config tables."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+
+def test_config_parser_contract(tmp_path):
+    from fast_b200 import conf
+    d = {'NITER': 10}
+    c = conf.ConfigParser(d)
+    assert c.config is d                      # kept by reference and completed in place
+    assert d['NCHUNKS'] == 10 and d['AO_MODE'] == 'AO' and d['DTHETA'] == [4, 0]
+    assert set(conf.DEFAULTS) <= set(d)
+    f = tmp_path / 'cfg.py'
+    f.write_text("p = {'NITER': 4, 'NCHUNKS': 2}\n")
+    c2 = conf.ConfigParser(str(f))
+    assert c2.config['NITER'] == 4 and c2.config['WVL'] == 1550e-9
+    with pytest.raises(Exception, match='Require .py config file'):
+        conf.ConfigParser('cfg.yaml')
+    with pytest.raises(Exception, match='Either config file name or params dict required'):
+        conf.ConfigParser(12)
+
+
+def test_turbulence_models_match_reference():
+    from fast_b200 import turbulence_models as tm
+    g, _ = load_golden('c2')
+    h, cn2, w = tm.HV57_Bufton_profile(4)
+    np.testing.assert_allclose(h, g['H_TURB'], rtol=1e-14)
+    np.testing.assert_allclose(cn2, g['CN2_TURB'], rtol=1e-14)
+    np.testing.assert_allclose(w, g['WIND_SPD'], rtol=1e-14)
+    hh = np.linspace(0, 20000, 10)
+    assert tm.HV57(hh).dtype == float and len(tm.Bufton_wind(hh)) == 10       # test/tests_pytest.py:12-27
+
+
+@pytest.mark.parametrize('name', ['mini_ao', 'mini_axicon', 'mini_up_w0', 'c1prime', 'c2', 'c4'])
+def test_pupil_and_mode_match_reference(name):
+    from fast_b200 import funcs
+    g, p = load_golden(name)
+    N, dx, npup = int(g['Npxls']), float(g['dx']), int(g['Npxls_pup'])
+    pupil = funcs.compute_pupil(N, dx, p['D_GROUND'], p['OBSC_GROUND'])
+    ptype = 'axicon' if p['AXICON'] else 'gauss'
+    mode, W0 = funcs.compute_gaussian_mode(pupil, dx, p['W0'], D=p['D_GROUND'], obsc=p['OBSC_GROUND'], ptype=ptype)
+    lo, hi = (N - npup) // 2, (N + npup) // 2
+    np.testing.assert_allclose(pupil[lo:hi, lo:hi], g['pupil'], rtol=1e-13)
+    np.testing.assert_allclose(mode[lo:hi, lo:hi], g['pupil_mode'], rtol=1e-9)
+    assert W0 == pytest.approx(float(g['W0']), rel=1e-10)
+
+
+def test_geometry_helpers():
+    from fast_b200 import funcs
+    g, p = load_golden('c3_el45')
+    assert funcs.l_path(550e3, p['ZENITH_ANGLE']) == pytest.approx(float(g['L']), rel=1e-13)
+    wc = funcs.calculate_wind_correction(g['h'], p['ANISO_DL'], p['TLOOP'])
+    assert wc.shape == (4, 2) and np.all(wc[:, 1] == 0)
+    with pytest.raises(TypeError, match="axicon"):
+        funcs.compute_gaussian_mode(np.ones((8, 8)), 0.1, 'opt', ptype='axicon')
+    with pytest.raises(Exception, match='ptype must be one of'):
+        funcs.compute_gaussian_mode(np.ones((8, 8)), 0.1, 0.2, ptype='bessel')
+
+
+@pytest.mark.parametrize('name', ['mini_tt', 'mini_modal', 'mini_ao'])
+def test_host_masks_match_reference(name):
+    from fast_b200 import ao_power_spectra as aps
+    from fast_b200.fast import SpatialFrequencies
+    g, p = load_golden(name)
+    freq = SpatialFrequencies(int(g['Npxls']), float(g['dx']))
+    zmax, modal = p['ZMAX'], p['MODAL']
+    if p['AO_MODE'] == 'TT':
+        zmax, modal = 3, True
+    m = aps.mask_lf(freq.main, p['DSUBAP'], modal=modal, modal_mult=p['MODAL_MULT'], Zmax=zmax, D=p['D_GROUND'])
+    np.testing.assert_allclose(np.asarray(m, dtype=float), g['lf_mask'], rtol=1e-12, atol=1e-15)
+
+
+def test_product_and_oracle_config_tables_agree():
+    from fast_b200 import configs as a
+    from oracle import configs as b
+    for f, kw in [('c2', {}), ('c4', {}), ('c5', {}), ('c1prime', {}), ('mini', {}),
+                  ('c3_elevation', {'el_deg': 30.})]:
+        pa, pb = getattr(a, f)(**kw), getattr(b, f)(**kw)
+        assert pa.keys() == pb.keys()
+        for k in pa:
+            assert np.all(np.asarray(pa[k] == pb[k])), (f, k)
+
+
+def test_fast_result_properties():
+    from fast_b200 import FastResult
+    r = np.array([0.5, 0.25, 1.0])
+    res = FastResult(r, 2e-6)
+    np.testing.assert_allclose(res.power, 2e-6 * r)
+    np.testing.assert_allclose(res.dB_rel, 10 * np.log10(r))
+    np.testing.assert_allclose(res.dBm, 10 * np.log10(r * 2e-6 / 1e-3))
+    assert res.scintillation_index == pytest.approx((r / r.mean()).var())
+    assert res.avg_power_dB_rel == pytest.approx(10 * np.log10(r.mean()))
+    assert 'Scintillation index' in str(res)
