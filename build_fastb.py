@@ -1,14 +1,17 @@
 """Builds fast_b200/libfastb.so in-tree with nvcc for sm_100a (B200).
 
-    python -m fast_b200.build [--force]
+    python build_fastb.py [--force]
 
+Lives outside the package on purpose: importing `fast_b200` loads the shared library (and fails
+loudly when it is missing or stale), so the build must not depend on that import.
 The .so is git-ignored but ships to the GPU box with the working tree."""
 import hashlib
 import os
 import subprocess
 import sys
 
-HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.abspath(__file__))
+HERE = os.path.join(ROOT, 'fast_b200')
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libfastb.so')
 STAMP = os.path.join(HERE, 'build', 'libfastb.stamp')
@@ -20,12 +23,13 @@ SOURCES = {
     'psd_build.cu': ['-fmad=false'],
     'screen_detect.cu': ['-Xptxas', '-v'],
     'stats.cu': [],
+    'temporal.cu': [],
 }
 
 
 def _digest():
     h = hashlib.sha256()
-    for root in (CSRC, os.path.join(os.path.dirname(HERE), 'include')):
+    for root in (CSRC, os.path.join(ROOT, 'include')):
         for f in sorted(os.listdir(root)):
             with open(os.path.join(root, f), 'rb') as fh:
                 h.update(f.encode())

@@ -4,7 +4,7 @@
     import fast_b200 as fast
     sim = fast.Fast(params); result = sim.run()
 
-Importing the package requires the in-tree CUDA library (python -m fast_b200.build)."""
+Importing the package requires the in-tree CUDA library (python build_fastb.py)."""
 from . import conf, funcs, turbulence_models, ao_power_spectra, dist   # noqa: F401
 from . import _lib                                                      # noqa: F401
 from .fast import Fast, FastResult, SpatialFrequencies, SpatialFrequencyStruct, load  # noqa: F401

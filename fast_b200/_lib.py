@@ -3,7 +3,7 @@
 PyTorch is used only to own device memory and streams; every wrapper takes torch CUDA tensors,
 passes their raw device pointers and the current stream, and raises `FastbError` on a non-zero
 return code.  There is no CPU fallback: importing this module fails loudly when the shared
-library has not been built (python -m fast_b200.build)."""
+library has not been built (python build_fastb.py)."""
 import ctypes as C
 import os
 
@@ -24,7 +24,7 @@ class FastbError(RuntimeError):
 if not os.path.exists(LIB_PATH):
     raise ImportError(
         f'{LIB_PATH} not found: the CUDA extension is required (no CPU fallback). '
-        'Build it with `python -m fast_b200.build` (needs nvcc, targets sm_100a).')
+        'Build it with `python build_fastb.py` (needs nvcc, targets sm_100a).')
 
 lib = C.CDLL(LIB_PATH)
 
@@ -60,6 +60,13 @@ class RunParams(C.Structure):
                 ('reserved_f', C.c_float)]
 
 
+class TemporalParams(C.Structure):
+    _fields_ = [('n', C.c_int32), ('n_pup', C.c_int32), ('n_layers', C.c_int32), ('coherent', C.c_int32),
+                ('n_steps', C.c_int64), ('u_sum', C.c_double)]
+
+
+LAYER_PAIR_BASE = 1 << 62
+
 # every symbol include/fastb.h declares (tests/test_abi.py checks the list against the header)
 _SIGS = {
     'fastb_psd_build': (C.c_int, [C.POINTER(PsdParams), C.POINTER(PsdInputs), C.POINTER(PsdOutputs), C.c_void_p]),
@@ -72,6 +79,10 @@ _SIGS = {
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     'fastb_rng_dump': (C.c_int, [C.c_uint64, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_int64,
                                  C.c_void_p, C.c_void_p]),
+    'fastb_layer_screens_workspace_bytes': (C.c_int64, [C.c_int32, C.c_int32]),
+    'fastb_layer_screens': (C.c_int, [C.c_int32, C.c_int32, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_int64, C.c_void_p]),
+    'fastb_temporal_detect': (C.c_int, [C.POINTER(TemporalParams)] + [C.c_void_p] * 8 + [C.c_void_p]),
     'fastb_stats': (C.c_int, [C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_int32, C.c_void_p,
                               C.c_void_p, C.c_void_p, C.c_void_p]),
     'fastb_version': (C.c_int, []),
@@ -194,3 +205,22 @@ def stats(r, db_lo, db_hi, nbins, sums, minmax, hist):
     _check(lib.fastb_stats(_ptr(r, torch.float32), r.numel(), float(db_lo), float(db_hi), int(nbins),
                            _ptr(sums, torch.float64), _ptr(minmax, torch.float64), _ptr(hist, torch.int64),
                            _stream()), 'fastb_stats')
+
+
+def layer_screens(weight_per_layer, seed, noise=None):
+    """K4a: (L, N, N) signed per-layer weights -> (L, N, N) float32 real screens."""
+    L, n = weight_per_layer.shape[0], weight_per_layer.shape[-1]
+    out = torch.empty((L, n, n), dtype=torch.float32, device=weight_per_layer.device)
+    nbytes = lib.fastb_layer_screens_workspace_bytes(n, L)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=out.device)
+    nz = None if noise is None else torch.view_as_real(noise.contiguous())
+    _check(lib.fastb_layer_screens(n, L, int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(weight_per_layer, torch.float32),
+                                   _ptr(nz), _ptr(out), _ptr(ws), nbytes, _stream()), 'fastb_layer_screens')
+    return out
+
+
+def temporal_detect(tp: TemporalParams, screens, xi, xf, yi, yf, U, chi, out):
+    f32, i32 = torch.float32, torch.int32
+    _check(lib.fastb_temporal_detect(C.byref(tp), _ptr(screens, f32), _ptr(xi, i32), _ptr(xf, f32),
+                                     _ptr(yi, i32), _ptr(yf, f32), _ptr(U, f32), _ptr(chi, f32),
+                                     _ptr(out, f32), _stream()), 'fastb_temporal_detect')

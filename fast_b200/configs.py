@@ -33,6 +33,11 @@ def _mk(**kw):
     return p
 
 
+def c1(seed=1):
+    """Config 1 verbatim: test/test_params.py (TEMPORAL uplink, N auto -> 164, NITER=100)."""
+    return _mk(SEED=seed)
+
+
 def c1prime(niter=100, nchunks=10, seed=1):
     """Config 1 with TEMPORAL off (test/tests_pytest.py:56-59): N auto -> 164."""
     return _mk(TEMPORAL=False, NITER=niter, NCHUNKS=nchunks, SEED=seed)

@@ -24,6 +24,7 @@ from . import ao_power_spectra
 from . import conf
 from . import dist
 from . import funcs
+from . import temporal
 
 logger = logging.getLogger(__name__)
 
@@ -32,20 +33,37 @@ _AO_MODES = {'NOAO': _lib.AO_NOAO, 'AO': _lib.AO_AO, 'TT': _lib.AO_AO, 'LGSAO': 
 
 class SpatialFrequencyStruct():
     """Centred angular-frequency grid (fast/fast.py:877-921): fx[r, c] = fx_axis[c],
-    fy[r, c] = fy_axis[r].  2-D arrays are built on first use; the device never reads them."""
+    fy[r, c] = fy_axis[r]; 2-D axes give one (optionally rotated) grid per layer.  The 2-D
+    arrays are built on first use; the device never reads them."""
 
-    def __init__(self, fx_axis, fy_axis=None):
+    def __init__(self, fx_axis, fy_axis=None, rot=None, freq_per_layer=False):
         self.fx_axis = fx_axis
         self.fy_axis = fx_axis if fy_axis is None else fy_axis
-        self.freq_per_layer = False
-        self.f = fx_axis
-        self.df = self.dfx = fx_axis[..., 1] - fx_axis[..., 0]
+        self.freq_per_layer = freq_per_layer
+        if fy_axis is None:
+            self.f = fx_axis
+            self.df = fx_axis[..., 1] - fx_axis[..., 0]
+        self.dfx = fx_axis[..., 1] - fx_axis[..., 0]
         self.dfy = self.fy_axis[..., 1] - self.fy_axis[..., 0]
+        if fx_axis.ndim not in (1, 2):
+            raise Exception('fx_axis ndim sould be either 1 or 2')
+        self._rot = rot
         self._grid = None
 
     def _mesh(self):
         if self._grid is None:
-            self._grid = numpy.meshgrid(self.fx_axis, self.fy_axis)
+            def one(ax, ay, angle):
+                gx, gy = numpy.meshgrid(ax, ay)
+                if angle is None:
+                    return gx, gy
+                return (gx * numpy.cos(angle) - gy * numpy.sin(angle),
+                        gx * numpy.sin(angle) + gy * numpy.cos(angle))
+            if self.fx_axis.ndim == 1:
+                self._grid = one(self.fx_axis, self.fy_axis, self._rot)
+            else:
+                pairs = [one(self.fx_axis[i], self.fy_axis[i], None if self._rot is None else self._rot[i])
+                         for i in range(self.fx_axis.shape[0])]
+                self._grid = (numpy.array([a for a, _ in pairs]), numpy.array([b for _, b in pairs]))
         return self._grid
 
     @property
@@ -62,7 +80,7 @@ class SpatialFrequencyStruct():
 
 
 class SpatialFrequencies():
-    """fast/fast.py:814-833: `main` grid with df = 2 pi / (N dx)."""
+    """fast/fast.py:814-875: `main` grid with df = 2 pi / (N dx); `temporal` per-layer grids."""
 
     def __init__(self, N, dx):
         self.N, self.dx = N, dx
@@ -73,6 +91,11 @@ class SpatialFrequencies():
     fx = property(lambda self: self.main.fx)
     fy = property(lambda self: self.main.fy)
     fabs = property(lambda self: self.main.fabs)
+
+    def make_temporal_freqs(self, nlayer, Ny, Nx, wind_speed, wind_dir, dt):
+        fx_axes, fy_axes = temporal.temporal_axes(nlayer, Ny, Nx, wind_speed, dt, self.main.dfy)
+        self.temporal = SpatialFrequencyStruct(fx_axes, fy_axes, rot=numpy.radians(wind_dir),
+                                               freq_per_layer=True)
 
 
 class Fast():
@@ -106,11 +129,7 @@ class Fast():
         self.Niter_per_chunk = self.Niter // self.Nchunks
         if not (self.Niter_per_chunk % 2 == 0) and not self.temporal:
             raise Exception('NITER/NCHUNKS must be even number')
-        if self.temporal:
-            raise NotImplementedError(
-                "TEMPORAL=True (frozen-flow time series, fast/fast.py:607-637) is not built on the "
-                "CUDA path yet; set TEMPORAL=False")
-        if self.params['SUBHARM']:
+        if self.params['SUBHARM'] and not self.temporal:
             raise NotImplementedError(
                 "SUBHARM=True (fast/funcs.py:225-258) is not built on the CUDA path yet")
 
@@ -216,7 +235,10 @@ class Fast():
                              numpy.pi / p['DSUBAP'] / 5])                         # corrected region
             n_nyq = int(2 * numpy.ceil(2 * numpy.pi / (nyq * self.dx) / 2))
             n_ap = int(2 * numpy.ceil(p['D_GROUND'] / self.dx / 2)) + 2
-            self.Npxls = int(numpy.max([n_nyq, n_ap]))
+            n_t = 0
+            if p['TEMPORAL']:       # enough pixels for the wind not to wrap during the run
+                n_t = int(p['WIND_SPD'].max() * p['DT'] * p['NITER'] / p['DX'] / 2)
+            self.Npxls = int(numpy.max([n_nyq, n_ap, n_t]))
             logger.info(f"Auto set NPXLS to {self.Npxls}")
             if p['AO_MODE'] == 'NOAO' and not numpy.isinf(p['L0']):
                 n_L0 = int(2 * numpy.ceil((p['L0'] * 2) / self.dx) / 2)
@@ -225,6 +247,13 @@ class Fast():
                                    f"Recommended NPXLS: {n_L0}")
         else:
             self.Npxls = int(p['NPXLS'])
+            if p['TEMPORAL']:
+                n_t = int(p['WIND_SPD'].max() * p['DT'] * p['NITER'] / p['DX'] / 2)
+                if self.Npxls < n_t:
+                    logger.warning("NPXLS is likely too small -- some periodicity may occur in your "
+                                   "resulting time series")
+                    logger.warning(f"Current value: {self.Npxls}")
+                    logger.warning(f"Recommended value: {n_t}")
         if self.Npxls % 2:
             raise Exception('NPXLS must be even')
         if self.Npxls > 2048:
@@ -234,6 +263,11 @@ class Fast():
             raise Exception('aperture does not fit in the grid: increase NPXLS or DX')
         self.freq = SpatialFrequencies(self.Npxls, self.dx)
         self.subharmonics = False
+        if self.temporal:
+            self.freq.make_temporal_freqs(len(self.h), self.Npxls, self.Niter, self.wind_speed,
+                                          self.wind_dir, self.dt)
+            if p['SUBHARM']:
+                logger.info("SUBHARM not used in TEMPORAL mode")
 
     def init_ao_params(self):
         p = self.params
@@ -278,6 +312,9 @@ class Fast():
         self.pup_coords = numpy.array((numpy.arange(lo, hi), numpy.arange(lo, hi))).astype(int)
         self.pupil = pupil_full[lo:hi, lo:hi]
         self.pupil_mode = mode_full[lo:hi, lo:hi]
+        if self.temporal:
+            ft = self.freq.temporal
+            self.pupil_filter_temporal = temporal.elongated_pupil_filter(self, ft.fx_axis, ft.fy_axis)
         return self.pupil
 
     def init_phs_logamp(self):
@@ -354,6 +391,9 @@ class Fast():
         outs = {'integrands': slab[0:3], 'noise': slab[3], 'powerspec': slab[4], 'logamp': slab[5],
                 'powerspec_per_layer': slab[6:], 'turb': d['turb'], 'g_ao': d['g_ao'],
                 'alias': d['alias'], 'weight': d['weight']}
+        if self.temporal:
+            d['weight_per_layer'] = torch.empty((L, N, N), dtype=torch.float32, device=dev)
+            outs['weight_per_layer'] = d['weight_per_layer']
         _lib.psd_build(self._psd_params(), outs, lf_mask=lf, zfilter=zf, pupil_filter=d['pupil_filter'])
         d['noise'], d['powerspec'], d['logamp'], d['powerspec_per_layer'] = slab[3], slab[4], slab[5], slab[6:]
         w = torch.from_numpy(funcs.simpson_weights(self.freq.main.f)).to(dev)
@@ -372,6 +412,13 @@ class Fast():
         U = numpy.ascontiguousarray(self.pupil * self.pupil_mode)
         self._u_sum = float(U.sum())
         d['U'] = torch.from_numpy(U.astype(numpy.float32)).to(dev)
+        if self.temporal:
+            # per-step wind shifts in pixels (fast/fast.py:543-544) and the temporal log-amp PSD
+            dts = numpy.arange(1, self.Niter_per_chunk + 1) * self.dt
+            self.pixel_shifts = dts * self.wind_vector[..., numpy.newaxis] / self.dx
+            ft = self.freq.temporal
+            self.temporal_logamp_powerspec = temporal.temporal_logamp_powerspec(
+                self, ft.fx_axis, ft.fy_axis, ft.fabs, self.pupil_filter_temporal)
 
     def _host(self, name):
         if name not in self._host_cache:
@@ -404,10 +451,15 @@ class Fast():
         rp.algo = algo
         rp.n_pairs, rp.first_pair = int(n_pairs), int(first_pair)
         rp.pairs_per_chunk = self.Niter_per_chunk // 2
-        rp.seed = int(self.seed) & 0xFFFFFFFFFFFFFFFF if self.seed != None else self._auto_seed()  # noqa: E711
+        rp.seed = self._run_seed()
         rp.u_sum = self._u_sum
         rp.sigma_chi = math.sqrt(self.logamp_var)
         return rp
+
+    def _run_seed(self):
+        if self.seed != None:  # noqa: E711
+            return int(self.seed) & 0xFFFFFFFFFFFFFFFF
+        return self._auto_seed()
 
     def _auto_seed(self):
         if not hasattr(self, '_seed_drawn'):
@@ -443,7 +495,19 @@ class Fast():
         """RNG='numpy': host draws in the reference's order (fast/fast.py:639-645);
         RNG='device': chi is generated inside the kernel and this only clears the buffer."""
         self.logamp[:] = 0
-        if self.rng_mode == 'numpy':
+        if self.temporal:
+            # temporally coloured chi: Niter complex draws + one 1-D FFT on the host
+            # (fast/funcs.py:367-375).  RNG='device' uses a generator derived from the seed.
+            keep = funcs._R
+            if self.rng_mode == 'device':
+                funcs._R = numpy.random.default_rng([self._run_seed(), 0xC41])
+            try:
+                self.logamp[:] = funcs.generate_random_coefficients_logamp(
+                    self.Niter, self.logamp_var, True, self.temporal_logamp_powerspec).real
+            finally:
+                funcs._R = keep
+            self._d['chi'] = torch.from_numpy(self.logamp.astype(numpy.float32)).to(self.device)
+        elif self.rng_mode == 'numpy':
             self.logamp[:] = funcs.generate_random_coefficients_logamp(self.Niter, self.logamp_var).real
             self._d['chi'] = torch.from_numpy(self.logamp.astype(numpy.float32)).to(self.device)
         else:
@@ -459,9 +523,41 @@ class Fast():
             self._d['noise'] = torch.from_numpy(rand).to(self.device)
         return None
 
+    def compute_phs_temporal(self, chunk=0):
+        """TEMPORAL mode (fast/fast.py:607-637).  Chunk 0: one real screen per layer on the
+        device (fastb_layer_screens).  Every chunk: the wind-shifted sample coordinates of its
+        J steps (host, tiny) staged on the device; the gather itself is fused with the detector."""
+        if chunk == 0:
+            noise = None
+            if self.rng_mode == 'numpy':
+                shape = (len(self.h), self.Npxls, self.Npxls)
+                noise = torch.from_numpy(funcs.generate_random_coefficients(shape).astype(numpy.complex64)).to(self.device)
+            self._d['layer_screens'] = _lib.layer_screens(self._d['weight_per_layer'], self._run_seed(), noise=noise)
+            self.interp_coords = self.pup_coords[numpy.newaxis, :, numpy.newaxis, :].astype(float) \
+                + self.pixel_shifts[:, :, :, numpy.newaxis]
+        coords = temporal.sample_coordinates(self.interp_coords, self.Npxls)
+        self._d['tcoords'] = tuple(torch.from_numpy(c).to(self.device) for c in coords)
+        self.interp_coords = self.interp_coords + self.pixel_shifts[:, :, -1, numpy.newaxis, numpy.newaxis]
+        return None
+
+    def _temporal_detector(self, chunk):
+        J = self.Niter_per_chunk
+        tp = _lib.TemporalParams()
+        tp.n, tp.n_pup, tp.n_layers = self.Npxls, self.Npxls_pup, len(self.h)
+        tp.coherent = 1 if self.params['COHERENT'] else 0
+        tp.n_steps, tp.u_sum = J, self._u_sum
+        out = torch.empty(J * (2 if tp.coherent else 1), dtype=torch.float32, device=self.device)
+        xi, xf, yi, yf = self._d['tcoords']
+        chi = self._d['chi'][chunk * J:(chunk + 1) * J].contiguous()
+        _lib.temporal_detect(tp, self._d['layer_screens'], xi, xf, yi, yf, self._d['U'], chi, out)
+        return torch.view_as_complex(out.view(-1, 2)) if tp.coherent else out
+
     def compute_detector(self, chunk=0):
         """Screens + detector for one chunk on the device; returns the chunk's J results in
         the reference's order [Re half | Im half] (fast/fast.py:647-668) as a device tensor."""
+        if self.temporal:
+            self.random_iters = self._temporal_detector(chunk)
+            return self.random_iters
         ppc = self.Niter_per_chunk // 2
         noise = self._d.get('noise') if self.rng_mode == 'numpy' else None
         a, b = self.screen_detect(chunk * ppc, ppc, noise=noise, chi=self._d.get('chi'))
@@ -475,7 +571,13 @@ class Fast():
         self.compute_logamp()
         ppc = self.Niter_per_chunk // 2
         total = self.Nchunks * ppc
-        if self.rng_mode == 'device':
+        if self.temporal:
+            parts = []
+            for i in range(self.Nchunks):
+                self.compute_phs_temporal(chunk=i)
+                parts.append(self.compute_detector(chunk=i))
+            flat = torch.cat(parts)
+        elif self.rng_mode == 'device':
             rank, world = dist.rank_world()
             lo, hi = dist.shard_range(total, rank, world)
             a, b = self.screen_detect(lo, hi - lo)

@@ -108,12 +108,17 @@ def generate_random_coefficients(shape):
 
 
 def generate_random_coefficients_logamp(Nscrns, powerspec, temporal=False, temporal_powerspecs=None):
-    """Log-amplitude draws scaled by sqrt(variance) (fast/funcs.py:358-365, non-temporal)."""
-    if temporal:
-        raise NotImplementedError("TEMPORAL log-amplitude colouring is not built yet")
-    shape = (Nscrns, *numpy.shape(powerspec))
-    rand = _R.normal(0, 1, size=shape) + 1j * _R.normal(0, 1, size=shape)
-    return rand * numpy.sqrt(powerspec)
+    """Log-amplitude draws scaled by sqrt(variance) (fast/funcs.py:358-375).  temporal=True:
+    complex noise coloured by the normalised temporal PSD, centred FFT along time."""
+    if not temporal:
+        shape = (Nscrns, *numpy.shape(powerspec))
+        rand = _R.normal(0, 1, size=shape) + 1j * _R.normal(0, 1, size=shape)
+        return rand * numpy.sqrt(powerspec)
+    shape = (*numpy.shape(powerspec), Nscrns)
+    spec = _R.normal(0, 1, size=shape) + 1j * _R.normal(0, 1, size=shape)
+    spec = spec * numpy.sqrt(temporal_powerspecs / temporal_powerspecs.sum())
+    series = numpy.fft.fftshift(numpy.fft.fft(numpy.fft.fftshift(spec, axes=-1)), axes=-1)
+    return series.T * numpy.sqrt(powerspec)
 
 
 def l_path(h_sat, zeta):

@@ -186,6 +186,47 @@ int fastb_rng_dump(uint64_t seed, int64_t pair, int32_t n, float* d_noise_tile,
                    int64_t chi_first, int64_t chi_count, float* d_chi_normals, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * K4: TEMPORAL (frozen-flow) mode -- Fast.compute_phs_temporal (fast/fast.py:607-637).
+ *
+ * K4a fastb_layer_screens: the chunk-0 branch (fast/fast.py:609-614): one full-size REAL screen
+ * per turbulence layer, screen_l = Re centred-inverse-DFT2(noise_l * sqrt(powerspec_per_layer_l) df)
+ * (funcs.make_phase_fft(double=False), fast/funcs.py:210-223).
+ *   d_weight_per_layer  L*N*N signed weights from fastb_psd_build
+ *   d_noise             NULL (device Philox; layer l uses pair index FASTB_LAYER_PAIR_BASE + l,
+ *                       same cell mapping as fastb_screen_detect) or L*N*N complex64
+ *   d_screens           L*N*N float
+ * Any even N <= 4096: pruning does not apply (the whole screen is needed), and this runs once
+ * per simulation, so it is a direct O(N^3) DFT in fp32.
+ *
+ * K4b fastb_temporal_detect: the per-step body (fast/fast.py:619-633) fused with
+ * Fast.compute_detector (fast/fast.py:647-668).  For step j and pupil pixel (a, b)
+ *   phi = sum_l bilinear(screen_l; row = xi[l,j,a] + xf[l,j,a], col = yi[l,j,b] + yf[l,j,b])
+ *   z_j = exp(chi_j) sum(U exp(i phi)) / sum(U);  out_j = |z_j|^2 or z_j (coherent)
+ * The (integer, fraction) sample coordinates, layout [L][n_steps][n_pup], are prepared by the
+ * host exactly as the reference does (wrap, sort, roll, FITPACK clamp at N-1), with
+ * 0 <= xi, yi <= N-2 and 0 <= xf, yf <= 1.
+ * ------------------------------------------------------------------------------------- */
+#define FASTB_LAYER_PAIR_BASE (1ULL << 62)
+
+int64_t fastb_layer_screens_workspace_bytes(int32_t n, int32_t n_layers);
+int fastb_layer_screens(int32_t n, int32_t n_layers, uint64_t seed, const float* d_weight_per_layer,
+                        const float* d_noise, float* d_screens, void* d_workspace,
+                        int64_t workspace_bytes, void* stream);
+
+typedef struct FastbTemporalParams {
+    int32_t n;                      /* N */
+    int32_t n_pup;                  /* Npxls_pup */
+    int32_t n_layers;               /* L */
+    int32_t coherent;               /* 0: |z|^2; 1: z (re, im) */
+    int64_t n_steps;                /* time steps in this call (one chunk) */
+    double u_sum;                   /* sum(U) */
+} FastbTemporalParams;
+
+int fastb_temporal_detect(const FastbTemporalParams* p, const float* d_screens, const int32_t* d_xi,
+                          const float* d_xf, const int32_t* d_yi, const float* d_yf, const float* d_U,
+                          const float* d_chi, float* d_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * K3: result statistics for the multi-GPU reduction (no reference equivalent; feeds the
  * FastResult summaries of fast/fast.py:949-994 without a full gather).
  * d_sums[8]   += { n, sum r, sum r^2, sum dB, sum dB^2, 0, 0, 0 }   (dB = 10 log10 r)

@@ -655,3 +655,147 @@ def run_mc_device_rng(init, seed, n_pairs, pairs_per_chunk, coherent=None):
         r = detector(phs, U, chi_all[[i_re, i_im]], coherent)
         out[i_re], out[i_im] = r[0], r[1]
     return out
+
+
+# --------------------------------------------------------------------------------------
+# TEMPORAL (frozen-flow) path: fast/fast.py:181-206,217-219,394-405,538-587,607-637,846-875;
+# fast/funcs.py:367-375.  L per-layer screens are drawn once; each time step samples them at the
+# pupil coordinates shifted by the layer wind, bilinearly, and sums the layers.
+# --------------------------------------------------------------------------------------
+def temporal_setup(init):
+    """Everything TEMPORAL adds to Fast.__init__: pixel shifts per step, the per-layer temporal
+    frequency grids, the elongated pupil filter spline and the temporal log-amplitude PSD."""
+    from scipy.interpolate import RectBivariateSpline
+    p, atm = init['params'], init['atm']
+    N, dx, npup, df = init['N'], init['dx'], init['Npup'], init['df']
+    niter, J = p['NITER'], p['NITER'] // p['NCHUNKS']
+    h, cn2, wind = atm['h'], atm['cn2'], atm['wind_vector']
+    L = len(h)
+    shifts = (np.arange(1, J + 1) * p['DT']) * wind[..., None] / dx            # (L, 2, J)  fast.py:543-544
+
+    # per-layer frequency grids: x axis LINEAR frequency 1/(Niter v dt) (sic), y axis = main axis,
+    # rotated by the wind direction (fast.py:846-864, 903-907)
+    fxa = np.array([np.arange(-niter / 2, niter / 2) * (1 / (niter * atm['wind_speed'][i] * p['DT']))
+                    for i in range(L)])
+    fya = np.array([np.arange(-N / 2, N / 2) * df for _ in range(L)])
+    rot = np.radians(atm['wind_dir'])
+    fabs = np.zeros((L, N, niter))
+    for i in range(L):
+        gx, gy = np.meshgrid(fxa[i], fya[i])
+        xr = gx * np.cos(rot[i]) - gy * np.sin(rot[i])
+        yr = gx * np.sin(rot[i]) + gy * np.cos(rot[i])
+        fabs[i] = np.sqrt(xr ** 2 + yr ** 2)
+
+    # elongated high-resolution pupil filter, as a bilinear spline (fast.py:394-405)
+    f_max = max(fxa.max(), fya.max())
+    dx_req = np.pi / f_max
+    n_req = int(2 * np.ceil(2 * np.pi / (df * dx_req) / 2))
+    ny = 2 * npup
+    D, obsc = p['D_GROUND'], p['OBSC_GROUND']
+    ap = disc(D / dx_req / 2, n_req) - disc(obsc / dx_req / 2, n_req)
+    assert (ny - n_req) % 2 == 0
+    if ny > n_req:
+        pad = (ny - n_req) // 2
+        ap = np.pad(ap, [(0, 0), (pad, pad)])
+    elif ny < n_req:
+        cut = (n_req - ny) // 2
+        ap = ap[:, cut:-cut]
+    pup_t = ap / np.sqrt(ap.sum() * dx_req ** 2)
+    W0 = init['W0']
+    yy, xx = np.meshgrid(np.arange(ny), np.arange(n_req))          # gaussian2d((n_req, ny), w)
+    w = W0 / dx_req / np.sqrt(2)
+    mode_t = np.exp(-(((ny / 2. - yy) / w) ** 2 + ((n_req / 2. - xx) / w) ** 2) / 2) \
+        * np.sqrt(2 / (np.pi * W0 ** 2)) / pup_t.max()
+    pf_t = pupil_filter(pup_t * mode_t)
+    fxl = np.arange(-n_req / 2., n_req / 2.) * (2 * np.pi / (n_req * dx_req))
+    fyl = np.arange(-ny / 2., ny / 2.) * (2 * np.pi / (ny * dx))
+    spline = RectBivariateSpline(fxl, fyl, pf_t, kx=1, ky=1, s=0)
+
+    # temporal log-amplitude PSD, integrated over the axis orthogonal to the wind (fast.py:582-587);
+    # the spline is sampled at (fy_axis, fx_axis) un-rotated, as the reference does
+    total = np.zeros((N, niter))
+    k = init['k']
+    for i in range(L):
+        ps = von_karman_base(fabs[i], p['L0'], p['l0']) * cn2[i] * 2 * np.pi * k ** 2
+        ps = ps * np.sin(p['WVL'] * h[i] * fabs[i] ** 2 / (4 * np.pi)) ** 2
+        total += ps * spline(fya[i], fxa[i])
+    tps = total.sum(-2) * df
+    return dict(pixel_shifts=shifts, temporal_logamp_powerspec=tps, J=J)
+
+
+def temporal_logamp(rng, niter, logamp_var, tps):
+    """Temporally coloured log-amplitude: centred FFT of coloured complex noise, real part
+    (fast/funcs.py:367-375 with aotools.ft)."""
+    rf = rng.normal(0, 1, size=(niter,)) + 1j * rng.normal(0, 1, size=(niter,))
+    rf = rf * np.sqrt(tps / tps.sum())
+    r = np.fft.fftshift(np.fft.fft(np.fft.fftshift(rf)))
+    return (r * np.sqrt(logamp_var)).real
+
+
+def layer_screens(noise, per_layer, df):
+    """L real screens from (L, N, N) complex noise coloured per layer (fast/fast.py:611-614,
+    make_phase_fft double=False)."""
+    ax = (-1, -2)
+    n = noise.shape[-1]
+    spec = noise * np.sqrt(per_layer) * df
+    return (np.fft.ifftshift(np.fft.ifft2(np.fft.ifftshift(spec, axes=ax)), axes=ax) * n ** 2).real
+
+
+def temporal_sample_coords(interp, N):
+    """Per layer/axis/step: the coordinates at which the reference evaluates the screen for
+    each output pixel (fast/fast.py:621-633): wrap mod N, sort, and 'un-sort' by rolling with
+    the argmax of the gaps (0 when there is no wrap).  NOTE the roll is one short of restoring
+    the original order when a wrap occurs -- reproduced here because it is what the reference
+    computes."""
+    coord = np.sort(interp % N, axis=-1)
+    gaps = np.abs(np.diff(coord, axis=-1))
+    sh = gaps.argmax(-1)
+    sh[np.isclose(gaps, 1).all(-1)] = 0
+    npup = coord.shape[-1]
+    idx = (np.arange(npup) + sh[..., None]) % npup
+    return np.take_along_axis(coord, idx, axis=-1)
+
+
+def bilinear_clamped(scr, x, y):
+    """Grid evaluation of a degree-1 spline on knots 0..N-1 at rows x, columns y; arguments
+    beyond N-1 are clamped (FITPACK bispev behaviour of RectBivariateSpline(kx=ky=1, s=0))."""
+    n = scr.shape[0]
+    def split(c):
+        c = np.minimum(c, n - 1.0)
+        i0 = np.minimum(np.floor(c).astype(int), n - 2)
+        return i0, c - i0
+    ix, fx = split(x)
+    iy, fy = split(y)
+    a = scr[np.ix_(ix, iy)] * (1 - fy) + scr[np.ix_(ix, iy + 1)] * fy
+    b = scr[np.ix_(ix + 1, iy)] * (1 - fy) + scr[np.ix_(ix + 1, iy + 1)] * fy
+    return a * (1 - fx)[:, None] + b * fx[:, None]
+
+
+def run_mc_temporal(init, rng, screens_hook=None):
+    """Fast.run() in TEMPORAL mode (fast/fast.py:115-140, 607-637).  Returns (_r, chi, last phs)."""
+    p = init['params']
+    niter, nch = p['NITER'], p['NCHUNKS']
+    ts = temporal_setup(init)
+    J, shifts = ts['J'], ts['pixel_shifts']
+    N, npup, lo, hi = init['N'], init['Npup'], init['lo'], init['hi']
+    coherent = bool(p['COHERENT'])
+    U = init['pupil'] * init['pupil_mode']
+    chi = temporal_logamp(rng, niter, init['logamp_var'], ts['temporal_logamp_powerspec'])
+    L = len(init['atm']['h'])
+    noise = draw_complex(rng, (L, N, N))
+    scr = layer_screens(noise, init['powerspec_per_layer'], init['df'])
+    if screens_hook is not None:
+        screens_hook(scr)
+    base = np.arange(lo, hi).astype(float)
+    interp = base[None, None, None, :] + shifts[:, :, :, None]                 # (L, 2, J, Pp)
+    out = np.zeros((nch, J), dtype=complex if coherent else float)
+    phs = None
+    for c in range(nch):
+        at = temporal_sample_coords(interp, N)
+        phs = np.zeros((J, npup, npup))
+        for i in range(L):
+            for j in range(J):
+                phs[j] += bilinear_clamped(scr[i], at[i, 0, j], at[i, 1, j])
+        out[c] = detector(phs, U, chi[c * J:(c + 1) * J], coherent)
+        interp = interp + shifts[:, :, -1, None, None]
+    return out.flatten(), chi, phs

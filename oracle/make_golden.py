@@ -43,6 +43,10 @@ CASES = {
     'c3_el85':       ('c3_elevation', {'el_deg': 85.0, 'niter': 4}, 'scalars'),
     'c4':            ('c4', {'niter': 4}, 'sub'),
     'c5':            ('c5', {'niter': 2}, 'sub'),
+    # TEMPORAL frozen-flow path (fast/fast.py:607-637): config 1 verbatim, and a 64x64 variant
+    'c1_temporal':   ('c1', {}, 'temporal'),
+    'mini_temporal': ('mini', {'TEMPORAL': True, 'NITER': 60, 'NCHUNKS': 3, 'DT': 0.002, 'COHERENT': True},
+                      'temporal'),
 }
 
 SCALARS = ['W0', 'W0_sat', 'dx', 'Npxls', 'Npxls_pup', 'L', 'paa', 'r0', 'theta0', 'tau0',
@@ -63,12 +67,21 @@ def run_case(name):
             guard['noise_shape'] = np.array(shape)
         return r
 
+    orig_fft = fast.funcs.make_phase_fft
+
+    def spy_fft(*a, **k):
+        out = orig_fft(*a, **k)
+        guard.setdefault('first_screens', out.copy())
+        return out
+
     fast.funcs.generate_random_coefficients = spy
+    fast.funcs.make_phase_fft = spy_fft
     try:
         sim = fast.Fast(dict(p))
         res = sim.run()
     finally:
         fast.funcs.generate_random_coefficients = orig
+        fast.funcs.make_phase_fft = orig_fft
 
     d = {'case_factory': np.array(factory), 'case_kwargs': np.array(repr(kw)),
          'r': res._r, 'logamp': sim.logamp.copy(), 'noise_head': guard['noise_head'],
@@ -81,6 +94,14 @@ def run_case(name):
          'link_budget_vals': np.array(list(sim.link_budget.values()), dtype=float),
          'pupil': sim.pupil, 'pupil_mode': sim.pupil_mode,
          'phs_last_re0': sim.phs[0].copy(), 'phs_last_im0': sim.phs[sim.Niter_per_chunk // 2].copy()}
+    if level == 'temporal':
+        d['pixel_shifts'] = sim.pixel_shifts
+        d['temporal_logamp_powerspec'] = sim.temporal_logamp_powerspec
+        d['layer_screens_sub'] = guard['first_screens'][:, ::2, ::2].copy()
+        d['powerspec_per_layer_sub'] = sim.powerspec_per_layer[:, ::2, ::2].copy()
+        d['phs_last_all'] = sim.phs.copy()
+        d['powerspec'] = sim.powerspec
+        d['logamp_powerspec'] = sim.logamp_powerspec
     for s in SCALARS:
         d[s] = np.float64(getattr(sim, s))
     N = sim.Npxls

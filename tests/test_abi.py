@@ -12,8 +12,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 @pytest.fixture(scope='module')
 def lib():
-    from fast_b200 import build
-    build.build()
+    import build_fastb
+    build_fastb.build()
     from fast_b200 import _lib
     return _lib
 

@@ -191,3 +191,39 @@ def test_stats_kernel(fast):
     h, _ = np.histogram(res.dB_rel, bins=450, range=(-40, 5))
     assert st['hist'][:450].sum() + st['hist'][450:].sum() == 4000
     assert np.abs(st['hist'][:450] - h).sum() <= 4      # bin-edge rounding only
+
+
+# ---------------------------------------------------------------------------------------------
+# TEMPORAL (frozen-flow) mode: config 1 verbatim (test/test_params.py) and a 64x64 coherent case
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('name', ['c1_temporal', 'mini_temporal'])
+def test_temporal_run_with_reference_noise_matches_reference(fast, name):
+    g, p = load_golden(name)
+    sim = fast.Fast(dict(p, RNG='numpy'))
+    check_scalars(sim, g)
+    np.testing.assert_allclose(sim.pixel_shifts, g['pixel_shifts'], rtol=1e-13, atol=1e-13)
+    assert rel(sim.temporal_logamp_powerspec, g['temporal_logamp_powerspec']) < 1e-10
+    assert rel(sim.powerspec_per_layer[:, ::2, ::2], g['powerspec_per_layer_sub']) < 1e-9
+    res = sim.run()
+    np.testing.assert_allclose(sim.logamp, g['logamp'], rtol=1e-9, atol=1e-14)
+    scr = sim._d['layer_screens'].cpu().numpy()
+    assert rel(scr[:, ::2, ::2], g['layer_screens_sub']) < 2e-6
+    want = g['r']
+    assert res._r.shape == want.shape
+    assert np.max(np.abs(res._r - want) / np.abs(want)) < RTOL_R
+
+
+def test_temporal_device_rng_screens_match_oracle(fast):
+    g, p = load_golden('mini_temporal')
+    sim = fast.Fast(dict(p, SEED=31))
+    res = sim.run()
+    assert np.isfinite(res._r).all() and res._r.dtype == complex
+    init = fo.build(p)
+    L, N = len(init['atm']['h']), init['N']
+    noise = np.stack([fo.device_noise_pair(31, (1 << 62) + l, N) for l in range(L)])
+    want = fo.layer_screens(noise, init['powerspec_per_layer'], init['df'])
+    got = sim._d['layer_screens'].cpu().numpy()
+    assert rel(got, want) < 2e-5
+    # same seed -> same time series; different seed -> different
+    np.testing.assert_array_equal(fast.Fast(dict(p, SEED=31)).run()._r, res._r)
+    assert not np.array_equal(fast.Fast(dict(p, SEED=32)).run()._r, res._r)

@@ -95,3 +95,24 @@ def test_fast_result_properties():
     assert res.scintillation_index == pytest.approx((r / r.mean()).var())
     assert res.avg_power_dB_rel == pytest.approx(10 * np.log10(r.mean()))
     assert 'Scintillation index' in str(res)
+
+
+@pytest.mark.parametrize('name', ['c1_temporal', 'mini_temporal'])
+def test_temporal_host_bookkeeping_matches_oracle(name):
+    """The product's TEMPORAL coordinate bookkeeping (wrap / sort / roll / clamp) against the
+    oracle restatement (itself pinned to the reference in test_oracle_vs_golden)."""
+    from fast_b200 import temporal
+    from oracle import fast_oracle as fo
+    g, p = load_golden(name)
+    N, npup = int(g['Npxls']), int(g['Npxls_pup'])
+    lo = (N - npup) // 2
+    shifts = g['pixel_shifts']
+    interp = np.arange(lo, lo + npup).astype(float)[None, None, None, :] + shifts[:, :, :, None]
+    for chunk in range(4):
+        xi, xf, yi, yf = temporal.sample_coordinates(interp, N)
+        at = fo.temporal_sample_coords(interp, N)
+        atc = np.minimum(at, N - 1.0)
+        np.testing.assert_allclose(xi + xf.astype(float), atc[:, 0], atol=2e-5)
+        np.testing.assert_allclose(yi + yf.astype(float), atc[:, 1], atol=2e-5)
+        assert xi.min() >= 0 and xi.max() <= N - 2 and 0 <= xf.min() and xf.max() <= 1
+        interp = interp + shifts[:, :, -1, None, None]

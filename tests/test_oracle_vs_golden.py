@@ -141,3 +141,31 @@ def test_device_noise_is_standard_normal():
     assert abs(chi.mean()) < 0.02 and abs(chi.var() - 1) < 0.03
     # sub-ranges are consistent with the whole (counter-based => any range recomputable)
     np.testing.assert_array_equal(fo.device_chi_normals(7, 1001, 50), chi[1001:1051])
+
+
+@pytest.mark.parametrize('name', ['c1_temporal', 'mini_temporal'])
+def test_temporal_path(name):
+    """TEMPORAL frozen-flow path (config 1 verbatim = c1_temporal)."""
+    g, p = load_golden(name)
+    init = fo.build(p)
+    check_init(g, init, ['powerspec', 'logamp_powerspec'])
+    ts = fo.temporal_setup(init)
+    np.testing.assert_allclose(ts['pixel_shifts'], g['pixel_shifts'], rtol=1e-13, atol=1e-13)
+    assert rel(ts['temporal_logamp_powerspec'], g['temporal_logamp_powerspec']) < 1e-11
+    assert rel(init['powerspec_per_layer'][:, ::2, ::2], g['powerspec_per_layer_sub']) < 1e-12
+    seen = {}
+    r, chi, phs = fo.run_mc_temporal(init, np.random.default_rng(p['SEED']), screens_hook=lambda s: seen.update(s=s))
+    assert rel(seen['s'][:, ::2, ::2], g['layer_screens_sub']) < 1e-11
+    np.testing.assert_allclose(chi, g['logamp'], rtol=1e-9, atol=1e-14)
+    assert rel(phs, g['phs_last_all']) < 1e-10
+    assert rel(r, g['r']) < 1e-10
+
+
+def test_bilinear_matches_scipy_spline_including_clamp():
+    from scipy.interpolate import RectBivariateSpline
+    rng = np.random.default_rng(2)
+    scr = rng.normal(size=(12, 12))
+    s = RectBivariateSpline(np.arange(12), np.arange(12), scr, kx=1, ky=1, s=0)
+    x = np.sort(rng.uniform(0, 12, 9))
+    y = np.sort(rng.uniform(0, 12, 7))
+    np.testing.assert_allclose(fo.bilinear_clamped(scr, x, y), s(x, y), rtol=1e-12, atol=1e-13)
