@@ -60,6 +60,11 @@ class RunParams(C.Structure):
                 ('reserved_f', C.c_float)]
 
 
+class Subharm(C.Structure):
+    _fields_ = [('d_weight', C.c_void_p), ('d_noise', C.c_void_p), ('d_ex', C.c_void_p),
+                ('d_ey', C.c_void_p), ('d_mean', C.c_void_p)]
+
+
 class TemporalParams(C.Structure):
     _fields_ = [('n', C.c_int32), ('n_pup', C.c_int32), ('n_layers', C.c_int32), ('coherent', C.c_int32),
                 ('n_steps', C.c_int64), ('u_sum', C.c_double)]
@@ -76,7 +81,8 @@ _SIGS = {
     'fastb_pupil_filter_workspace_bytes': (C.c_int64, [C.c_int32]),
     'fastb_screen_detect_workspace_bytes': (C.c_int64, [C.POINTER(RunParams)]),
     'fastb_screen_detect': (C.c_int, [C.POINTER(RunParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+                                      C.POINTER(Subharm), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                      C.c_void_p]),
     'fastb_rng_dump': (C.c_int, [C.c_uint64, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_int64,
                                  C.c_void_p, C.c_void_p]),
     'fastb_layer_screens_workspace_bytes': (C.c_int64, [C.c_int32, C.c_int32]),
@@ -185,10 +191,16 @@ def screen_detect_workspace_bytes(rp: RunParams):
     return int(nbytes)
 
 
-def screen_detect(rp: RunParams, weight, U, out_a, out_b, workspace, chi=None, noise=None):
+def screen_detect(rp: RunParams, weight, U, out_a, out_b, workspace, chi=None, noise=None, subharm=None):
+    """subharm: None or dict(weight=(27,) f32, ex=(3,Pp,2) f32, ey=(3,Pp,2) f32, mean=(27,2) f32,
+    noise=None | (n_pairs,27,2) f32) of CUDA tensors."""
     f32 = torch.float32
+    sh = None
+    if subharm is not None:
+        sh = C.byref(Subharm(_ptr(subharm['weight'], f32), _ptr(subharm.get('noise'), f32),
+                             _ptr(subharm['ex'], f32), _ptr(subharm['ey'], f32), _ptr(subharm['mean'], f32)))
     _check(lib.fastb_screen_detect(C.byref(rp), _ptr(weight, f32), _ptr(U, f32), _ptr(chi, f32),
-                                   _ptr(noise), _ptr(out_a, f32), _ptr(out_b, f32), _ptr(workspace),
+                                   _ptr(noise), sh, _ptr(out_a, f32), _ptr(out_b, f32), _ptr(workspace),
                                    workspace.numel() * workspace.element_size(), _stream()),
            'fastb_screen_detect')
 

@@ -35,6 +35,7 @@ constexpr uint32_t kPhiloxW0 = 0x9E3779B9u;
 constexpr uint32_t kPhiloxW1 = 0xBB67AE85u;
 constexpr uint32_t kStreamNoise = 0x5CE7E000u;
 constexpr uint32_t kStreamChi = 0x10CA3900u;
+constexpr uint32_t kStreamSubharm = 0x5AB4A200u;
 
 // Philox4x32-10 (Salmon et al. SC'11).  Key schedule is uniform across the warp.
 __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,

@@ -280,7 +280,7 @@ using namespace fastb;
 extern "C" int fastb_psd_build(const FastbPsdParams* p, const FastbPsdInputs* in,
                                const FastbPsdOutputs* out, void* stream) {
     FASTB_REQUIRE(p && out, "fastb_psd_build: NULL params/outputs");
-    FASTB_REQUIRE(p->n >= 4 && (p->n % 2) == 0, "fastb_psd_build: n=%d must be even and >= 4", p->n);
+    FASTB_REQUIRE(p->n >= 2, "fastb_psd_build: n=%d must be >= 2", p->n);
     FASTB_REQUIRE(p->n_layers >= 1 && p->n_layers <= FASTB_MAX_LAYERS,
                   "fastb_psd_build: n_layers=%d outside 1..%d", p->n_layers, FASTB_MAX_LAYERS);
     FASTB_REQUIRE(p->ao_mode >= FASTB_AO_NOAO && p->ao_mode <= FASTB_AO_LGSAO,

@@ -32,7 +32,91 @@ struct RunArgs {
     float* out_b;
     float2* scratch;          // gridDim.x slots of n*n_pup float2
     int rows_per_block;       // direct kernel only
+    // sub-harmonics (NULL weight = off)
+    const float* sh_weight;   // 27
+    const float2* sh_noise;   // n_pairs*27 or NULL
+    const float2* sh_ex;      // 3*n_pup
+    const float2* sh_ey;      // 3*n_pup
+    const float2* sh_mean;    // 27
 };
+
+// ---- sub-harmonic term (include/fastb.h FastbSubharm) ------------------------------------
+// Per pair: 27 amplitudes -> per pupil row a table of 7 complex numbers
+//   tab[r] = { B, A_0[-], A_0[+], A_1[-], A_1[+], A_2[-], A_2[+] },
+//   A_i[s](r) = sum_q amp_i[q][s] Ey_i[q](r),  B = sum_i A_i[0](r) - grid mean,
+// so that a pixel costs 6 complex MACs: phi_sh = B + sum_i (A_i[-] conj(Ex_i) + A_i[+] Ex_i).
+constexpr int kShTab = 7;
+
+__device__ __forceinline__ float2 cmac(float2 acc, float2 a, float2 b) {
+    acc.x = fmaf(a.x, b.x, fmaf(-a.y, b.y, acc.x));
+    acc.y = fmaf(a.x, b.y, fmaf(a.y, b.x, acc.y));
+    return acc;
+}
+__device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
+
+// amp: 28 float2 in shared memory (27 amplitudes + the mean), tab: n_pup*7 float2.
+// Ends with the table complete only after the caller's next __syncthreads().
+__device__ void sh_prepare(const RunArgs& a, long long pair, float2* amp, float2* tab) {
+    const int tid = threadIdx.x;
+    const unsigned long long g = (unsigned long long)(a.first_pair + pair);
+    if (tid < 14) {
+        float2 n0, n1;
+        if (a.sh_noise) {
+            n0 = a.sh_noise[pair * 27 + 2 * tid];
+            n1 = (2 * tid + 1 < 27) ? a.sh_noise[pair * 27 + 2 * tid + 1] : make_float2(0.f, 0.f);
+        } else {
+            const uint4 w = philox4x32_10((uint32_t)tid, (uint32_t)g, (uint32_t)(g >> 32), kStreamSubharm,
+                                          (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+            n0 = box_muller(w.x, w.y);
+            n1 = box_muller(w.z, w.w);
+        }
+        const float w0 = a.sh_weight[2 * tid];
+        amp[2 * tid] = make_float2(n0.x * w0, n0.y * w0);
+        if (2 * tid + 1 < 27) {
+            const float w1 = a.sh_weight[2 * tid + 1];
+            amp[2 * tid + 1] = make_float2(n1.x * w1, n1.y * w1);
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float2 m = make_float2(0.f, 0.f);
+        for (int k = 0; k < 27; ++k) m = cmac(m, amp[k], a.sh_mean[k]);
+        amp[27] = m;
+    }
+    __syncthreads();
+    const int P = a.n_pup;
+    for (int r = tid; r < P; r += blockDim.x) {
+        float2 B = make_float2(-amp[27].x, -amp[27].y);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const float2 ey = a.sh_ey[i * P + r], eyc = cconj(ey);
+            const float2* ai = amp + i * 9;           // [q][s]
+#pragma unroll
+            for (int sx = 0; sx < 3; ++sx) {
+                float2 acc = ai[3 + sx];              // q = 1: fy = 0
+                acc = cmac(acc, ai[sx], eyc);         // q = 0: fy = -df
+                acc = cmac(acc, ai[6 + sx], ey);      // q = 2: fy = +df
+                if (sx == 1) {
+                    B.x += acc.x;
+                    B.y += acc.y;
+                } else {
+                    tab[r * kShTab + 1 + 2 * i + (sx == 2)] = acc;
+                }
+            }
+        }
+        tab[r * kShTab] = B;
+    }
+}
+
+__device__ __forceinline__ float2 sh_phase(const float2* tabrow, const float2 (&ex)[3]) {
+    float2 p = tabrow[0];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        p = cmac(p, tabrow[1 + 2 * i], cconj(ex[i]));
+        p = cmac(p, tabrow[2 + 2 * i], ex[i]);
+    }
+    return p;
+}
 
 // accumulate U exp(i s phi) for the two screens carried by one complex sample; us = s * u with
 // s = +-1 the output sign of the centred transform (cos is even, so only the sine terms see it).
@@ -125,8 +209,14 @@ __device__ __forceinline__ void line_fft(int u, float2 (&v)[16], const float2* t
 // [0, n1) are frequency rows (noise -> FFT -> pruned store to T[c][r']), iterations [n1, n1+n2)
 // are kept columns (load T[c][:] -> FFT -> detector accumulation).  No CTA-wide barrier inside a
 // pass when a line fits in a warp (N <= 512).
-template <int LOG2N, bool RNG, int MINB>
-__global__ void __launch_bounds__(kThreads, MINB) screen_detect_radix(const __grid_constant__ RunArgs a) {
+// CTAs per SM (register budget): measured on B200 (profiles/), 3 CTAs/SM (<= 80 registers, no
+// spills) is best except at N = 512, where 2 CTAs/SM with 124 registers wins.
+template <int LOG2N>
+constexpr int radix_min_blocks() { return LOG2N == 9 ? 2 : 3; }
+
+template <int LOG2N, bool RNG, bool SH>
+__global__ void __launch_bounds__(kThreads, radix_min_blocks<LOG2N>())
+screen_detect_radix(const __grid_constant__ RunArgs a) {
     using F = LineFFT<LOG2N>;
     constexpr int N = F::N, S1 = F::S1, LPB = kThreads / S1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -134,6 +224,8 @@ __global__ void __launch_bounds__(kThreads, MINB) screen_detect_radix(const __gr
     float2* twb = twa + F::kTwA;
     float2* bufs = twb + F::kTwB;
     float* red = reinterpret_cast<float*>(bufs + LPB * F::kBuf);
+    float2* sh_amp = reinterpret_cast<float2*>(red + 4 * (kThreads / 32));     // SH only
+    float2* sh_tab = sh_amp + 28;
 
     const int tid = threadIdx.x;
     const int ln = tid / S1, u = tid % S1;
@@ -164,6 +256,7 @@ __global__ void __launch_bounds__(kThreads, MINB) screen_detect_radix(const __gr
     for (long long pair = blockIdx.x; pair < a.n_pairs; pair += gridDim.x) {
         const unsigned long long g = (unsigned long long)(a.first_pair + pair);
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        if (SH) sh_prepare(a, pair, sh_amp, sh_tab);   // table visible after the barrier at it == n1
         for (int it = 0; it < n1 + n2; ++it) {
             const bool rows = it < n1;
             if (it == n1) __syncthreads();            // every row of T is stored before a column is read
@@ -205,11 +298,21 @@ __global__ void __launch_bounds__(kThreads, MINB) screen_detect_radix(const __gr
                 const float* ub = a.u_t + ((long long)line * P + kb);
                 // output sign (-1)^(r + c): k_off is even, so it is one value per thread and line
                 const float sgn = ((F::k_base(u) + line + lo) & 1) ? -1.f : 1.f;
+                float2 ex[3];
+                if (SH) {
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) ex[i] = __ldg(a.sh_ex + i * P + line);
+                }
 #pragma unroll
                 for (int e = 0; e < 16; ++e) {
                     if (need & (1u << e)) {
                         const float uu = __ldg(ub + F::k_off(e));
-                        accumulate(v[e], uu, uu * sgn, acc);
+                        if (SH) {
+                            const float2 sp = sh_phase(sh_tab + (kb + F::k_off(e)) * kShTab, ex);
+                            accumulate(make_float2(fmaf(sgn, v[e].x, sp.x), fmaf(sgn, v[e].y, sp.y)), uu, uu, acc);
+                        } else {
+                            accumulate(v[e], uu, uu * sgn, acc);
+                        }
                     }
                 }
             }
@@ -219,13 +322,15 @@ __global__ void __launch_bounds__(kThreads, MINB) screen_detect_radix(const __gr
 }
 
 // ---- general even N: pruned direct DFT (slow path; also used for N not a power of two) ----
-template <bool RNG>
+template <bool RNG, bool SH>
 __global__ void __launch_bounds__(kThreads) screen_detect_direct(const __grid_constant__ RunArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = a.n, P = a.n_pup, lo = a.lo, R = a.rows_per_block;
     float2* tw = reinterpret_cast<float2*>(smem_raw);
     float2* rows = tw + N;                       // R x N coloured noise
     float* red = reinterpret_cast<float*>(rows + (size_t)R * N);
+    float2* sh_amp = reinterpret_cast<float2*>(red + 4 * (kThreads / 32));     // SH only
+    float2* sh_tab = sh_amp + 28;
     const int tid = threadIdx.x;
 
     for (int j = tid; j < N; j += kThreads) {
@@ -241,6 +346,7 @@ __global__ void __launch_bounds__(kThreads) screen_detect_direct(const __grid_co
 
     for (long long pair = blockIdx.x; pair < a.n_pairs; pair += gridDim.x) {
         const unsigned long long g = (unsigned long long)(a.first_pair + pair);
+        if (SH) sh_prepare(a, pair, sh_amp, sh_tab);    // followed by barriers in the row loop
         for (int row0 = 0; row0 < N; row0 += R) {
             const int nr = min(R, N - row0);
             if (RNG) {
@@ -294,7 +400,14 @@ __global__ void __launch_bounds__(kThreads) screen_detect_direct(const __grid_co
                 if (ti >= N) ti -= N;
             }
             const float uu = a.u_t[(size_t)c * P + rr];
-            accumulate(make_float2(sr, si), uu, ((kk + c + lo) & 1) ? -uu : uu, acc);
+            if (SH) {
+                const float sgn = ((kk + c + lo) & 1) ? -1.f : 1.f;
+                const float2 ex[3] = {a.sh_ex[c], a.sh_ex[P + c], a.sh_ex[2 * P + c]};
+                const float2 sp = sh_phase(sh_tab + rr * kShTab, ex);
+                accumulate(make_float2(fmaf(sgn, sr, sp.x), fmaf(sgn, si, sp.y)), uu, uu, acc);
+            } else {
+                accumulate(make_float2(sr, si), uu, ((kk + c + lo) & 1) ? -uu : uu, acc);
+            }
         }
         finish_pair(a, pair, acc, red);
     }
@@ -323,20 +436,23 @@ __global__ void rng_dump_kernel(unsigned long long seed, unsigned long long g, i
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+size_t sh_smem_bytes(bool sh, int n_pup) { return sh ? sizeof(float2) * (28 + (size_t)kShTab * n_pup) : 0; }
+
 template <int LOG2N>
-size_t radix_smem_bytes() {
+size_t radix_smem_bytes(bool sh, int n_pup) {
     using F = LineFFT<LOG2N>;
     const int LPB = kThreads / F::S1;
     return sizeof(float2) * ((size_t)F::kTwA + F::kTwB + (size_t)LPB * F::kBuf) +
-           sizeof(float) * 4 * (kThreads / 32);
+           sizeof(float) * 4 * (kThreads / 32) + sh_smem_bytes(sh, n_pup);
 }
 
 int direct_rows(int n) {
     int r = (int)((96 * 1024) / ((size_t)n * sizeof(float2)));
     return r < 1 ? 1 : (r > 8 ? 8 : r);
 }
-size_t direct_smem_bytes(int n) {
-    return sizeof(float2) * ((size_t)n + (size_t)direct_rows(n) * n) + sizeof(float) * 4 * (kThreads / 32);
+size_t direct_smem_bytes(int n, bool sh, int n_pup) {
+    return sizeof(float2) * ((size_t)n + (size_t)direct_rows(n) * n) + sizeof(float) * 4 * (kThreads / 32) +
+           sh_smem_bytes(sh, n_pup);
 }
 
 bool radix_ok(int n) { return n >= 64 && n <= 2048 && (n & (n - 1)) == 0; }
@@ -350,12 +466,13 @@ int sm_count(int* out) {
 
 constexpr int kMaxCtasPerSm = 4;
 
-int g_min_blocks = 0;      // 0 = default; FASTB_MIN_BLOCKS env (2 or 3) selects the register budget
-
-template <int LOG2N, int MINB>
-int launch_radix_mb(const RunArgs& args, bool rng, int max_grid, cudaStream_t st) {
-    const size_t smem = radix_smem_bytes<LOG2N>();
-    auto kern = rng ? screen_detect_radix<LOG2N, true, MINB> : screen_detect_radix<LOG2N, false, MINB>;
+template <int LOG2N>
+int launch_radix(const RunArgs& args, bool rng, int max_grid, cudaStream_t st) {
+    const bool sh = args.sh_weight != nullptr;
+    const size_t smem = radix_smem_bytes<LOG2N>(sh, args.n_pup);
+    void (*kern)(RunArgs) = nullptr;
+    if (sh) kern = rng ? screen_detect_radix<LOG2N, true, true> : screen_detect_radix<LOG2N, false, true>;
+    else kern = rng ? screen_detect_radix<LOG2N, true, false> : screen_detect_radix<LOG2N, false, false>;
     FASTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     FASTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                                     cudaSharedmemCarveoutMaxShared));
@@ -373,21 +490,6 @@ int launch_radix_mb(const RunArgs& args, bool rng, int max_grid, cudaStream_t st
     if (grid > max_grid) grid = max_grid;
     kern<<<(unsigned)grid, kThreads, smem, st>>>(args);
     return check_launch("screen_detect_radix");
-}
-
-template <int LOG2N>
-int launch_radix(const RunArgs& args, bool rng, int max_grid, cudaStream_t st) {
-    if (g_min_blocks == 0) {
-        const char* e = getenv("FASTB_MIN_BLOCKS");
-        const int v = e ? atoi(e) : -1;
-        g_min_blocks = (v >= 2 && v <= 4) ? v : -1;
-    }
-    // measured on B200 (profiles/): 3 CTAs/SM (<= 80 registers, no spills) is best except at
-    // N = 512, where 2 CTAs/SM with 124 registers wins
-    const int mb = g_min_blocks > 0 ? g_min_blocks : (LOG2N == 9 ? 2 : 3);
-    if (mb == 2) return launch_radix_mb<LOG2N, 2>(args, rng, max_grid, st);
-    if (mb == 3) return launch_radix_mb<LOG2N, 3>(args, rng, max_grid, st);
-    return launch_radix_mb<LOG2N, 4>(args, rng, max_grid, st);
 }
 
 }  // namespace
@@ -428,9 +530,9 @@ extern "C" int64_t fastb_screen_detect_workspace_bytes(const FastbRunParams* p) 
 }
 
 extern "C" int fastb_screen_detect(const FastbRunParams* p, const float* d_weight, const float* d_U,
-                                   const float* d_chi, const float* d_noise, float* d_out_a,
-                                   float* d_out_b, void* d_workspace, int64_t workspace_bytes,
-                                   void* stream) {
+                                   const float* d_chi, const float* d_noise, const FastbSubharm* sh,
+                                   float* d_out_a, float* d_out_b, void* d_workspace,
+                                   int64_t workspace_bytes, void* stream) {
     int rc = validate_run(p);
     if (rc) return rc;
     FASTB_REQUIRE(d_weight && d_U && d_out_a && d_out_b && d_workspace, "fastb_screen_detect: NULL pointer");
@@ -462,6 +564,19 @@ extern "C" int fastb_screen_detect(const FastbRunParams* p, const float* d_weigh
     a.out_b = d_out_b;
     a.scratch = (float2*)((char*)d_workspace + ut);
     a.rows_per_block = direct_rows(p->n);
+    a.sh_weight = nullptr;
+    a.sh_noise = a.sh_ex = a.sh_ey = a.sh_mean = nullptr;
+    if (sh) {
+        FASTB_REQUIRE(sh->d_weight && sh->d_ex && sh->d_ey && sh->d_mean,
+                      "fastb_screen_detect: sub-harmonic tables must not be NULL");
+        FASTB_REQUIRE((sh->d_noise == nullptr) == (d_noise == nullptr),
+                      "fastb_screen_detect: d_noise and sh->d_noise must both be given or both be NULL");
+        a.sh_weight = sh->d_weight;
+        a.sh_noise = (const float2*)sh->d_noise;
+        a.sh_ex = (const float2*)sh->d_ex;
+        a.sh_ey = (const float2*)sh->d_ey;
+        a.sh_mean = (const float2*)sh->d_mean;
+    }
 
     const int pp = p->n_pup * p->n_pup;
     transpose_u_kernel<<<(pp + 255) / 256, 256, 0, st>>>(d_U, p->n_pup, (float*)d_workspace);
@@ -480,8 +595,11 @@ extern "C" int fastb_screen_detect(const FastbRunParams* p, const float* d_weigh
             default: break;
         }
     }
-    const size_t smem = direct_smem_bytes(p->n);
-    auto kern = rng ? screen_detect_direct<true> : screen_detect_direct<false>;
+    const bool has_sh = sh != nullptr;
+    const size_t smem = direct_smem_bytes(p->n, has_sh, p->n_pup);
+    void (*kern)(RunArgs) = nullptr;
+    if (has_sh) kern = rng ? screen_detect_direct<true, true> : screen_detect_direct<false, true>;
+    else kern = rng ? screen_detect_direct<true, false> : screen_detect_direct<false, false>;
     FASTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int sms = 0;
     if ((rc = sm_count(&sms))) return rc;

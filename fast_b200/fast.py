@@ -92,6 +92,12 @@ class SpatialFrequencies():
     fy = property(lambda self: self.main.fy)
     fabs = property(lambda self: self.main.fabs)
 
+    def make_subharm_freqs(self, pmax=3):
+        """Three 3 x 3 levels spaced 2 pi / (3^p N dx) (fast/fast.py:835-844)."""
+        D = self.dx * self.N
+        self.subharm = SpatialFrequencyStruct(
+            numpy.array([numpy.arange(-1, 2) * (2 * numpy.pi / (3 ** p * D)) for p in range(1, pmax + 1)]))
+
     def make_temporal_freqs(self, nlayer, Ny, Nx, wind_speed, wind_dir, dt):
         fx_axes, fy_axes = temporal.temporal_axes(nlayer, Ny, Nx, wind_speed, dt, self.main.dfy)
         self.temporal = SpatialFrequencyStruct(fx_axes, fy_axes, rot=numpy.radians(wind_dir),
@@ -129,10 +135,6 @@ class Fast():
         self.Niter_per_chunk = self.Niter // self.Nchunks
         if not (self.Niter_per_chunk % 2 == 0) and not self.temporal:
             raise Exception('NITER/NCHUNKS must be even number')
-        if self.params['SUBHARM'] and not self.temporal:
-            raise NotImplementedError(
-                "SUBHARM=True (fast/funcs.py:225-258) is not built on the CUDA path yet")
-
         _lib.require_cuda()
         dev = self.params.get('DEVICE', None)
         self.device = torch.device(dev) if dev is not None else torch.device('cuda', torch.cuda.current_device())
@@ -268,6 +270,9 @@ class Fast():
                                           self.wind_dir, self.dt)
             if p['SUBHARM']:
                 logger.info("SUBHARM not used in TEMPORAL mode")
+        elif p['SUBHARM']:
+            self.subharmonics = True
+            self.freq.make_subharm_freqs()
 
     def init_ao_params(self):
         p = self.params
@@ -348,16 +353,16 @@ class Fast():
         return self.link_budget
 
     # ------------------------------------------------------------------ K1 on the device
-    def _psd_params(self):
+    def _psd_params(self, n=None, df=None):
         pp = _lib.PsdParams()
         L = len(self.h)
         if L > _lib.MAX_LAYERS:
             raise Exception(f'at most {_lib.MAX_LAYERS} turbulence layers are supported')
-        pp.n, pp.n_layers = self.Npxls, L
+        pp.n, pp.n_layers = (self.Npxls if n is None else n), L
         pp.ao_mode = _AO_MODES[self.ao_mode]
         pp.alias = 1 if self.alias else 0
         pp.lmax = pp.kmax = 5
-        pp.df = float(self.freq.main.df)
+        pp.df = float(self.freq.main.df if df is None else df)
         pp.k, pp.wvl = float(self.k), float(self.wvl)
         pp.L0, pp.l0 = float(self.L0), float(self.l0)
         pp.dsubap, pp.tloop, pp.texp = float(self.Dsubap), float(self.tloop), float(self.texp)
@@ -407,6 +412,8 @@ class Fast():
         self.logamp_var = float(ints[5])
         self.phs_var_weights = ints[6:] / self.phs_var
         self.powerspec_subharm = self.phs_var_subharm = self.phs_var_weights_sh = None
+        if self.subharmonics:
+            self._compute_powerspec_subharm()
         self.temporal_powerspec = self.temporal_logamp_powerspec = None
         self.shifts = self.shifts_sh = None
         U = numpy.ascontiguousarray(self.pupil * self.pupil_mode)
@@ -419,6 +426,45 @@ class Fast():
             ft = self.freq.temporal
             self.temporal_logamp_powerspec = temporal.temporal_logamp_powerspec(
                 self, ft.fx_axis, ft.fy_axis, ft.fabs, self.pupil_filter_temporal)
+
+    def _compute_powerspec_subharm(self):
+        """Residual PSD on the three 3 x 3 sub-harmonic levels (fast/fast.py:494-531): the same
+        K1 kernel with N = 3 and the level's spacing, plus the plane-wave tables K2 needs."""
+        dev, L, f64 = self.device, len(self.h), torch.float64
+        sub = self.freq.subharm
+        lf_all = zf_all = None
+        if self.modal:
+            lf_all = numpy.asarray(ao_power_spectra.mask_lf(sub, self.Dsubap, modal=self.modal,
+                                                            modal_mult=self.modal_mult, Zmax=self.Zmax,
+                                                            D=self.D_ground), dtype=float)
+        if self.ao_mode == 'LGSAO':
+            zf_all = ao_power_spectra.zernike_squared_filter(sub.fabs, sub.fx, sub.fy, self.D_ground, 4).real
+        W = torch.zeros((3, 3, 3), dtype=f64, device=dev)
+        per_layer = torch.zeros((3, L, 3, 3), dtype=f64, device=dev)
+        for i in range(3):
+            lf = None if lf_all is None else torch.from_numpy(numpy.ascontiguousarray(lf_all[i])).to(dev)
+            zf = None if zf_all is None else torch.from_numpy(numpy.ascontiguousarray(zf_all[i])).to(dev)
+            _lib.psd_build(self._psd_params(n=3, df=sub.df[i]),
+                           {'powerspec': W[i], 'powerspec_per_layer': per_layer[i]}, lf_mask=lf, zfilter=zf)
+        self.powerspec_subharm = W.cpu().numpy()
+        self.powerspec_subharm_per_layer = per_layer.cpu().numpy().transpose(1, 0, 2, 3).copy()
+        self.phs_var_subharm = self.powerspec_subharm_per_layer.sum((-1, -2)) * sub.df ** 2
+        self.phs_var_weights_sh = self.phs_var_subharm / self.phs_var_subharm.sum()
+        # plane-wave tables for K2 (fast/funcs.py:227-253): pixel coordinates, per-level phasors
+        # on the pupil window, and the full-grid mean of each of the 27 waves
+        N, lo, P = self.Npxls, self._lo, self.Npxls_pup
+        D = self.dx * N
+        coords = numpy.arange(-D / 2, D / 2, self.dx)[:N]
+        phasor = numpy.exp(1j * coords[None, :] * sub.df[:, None])                  # (3, N): f = +df_i
+        grid_mean = numpy.stack([phasor.conj().mean(1), numpy.ones(3), phasor.mean(1)], axis=1)   # [i][s]
+        mean27 = grid_mean[:, None, :] * grid_mean[:, :, None]                       # [i][q][s]
+        weight27 = numpy.sqrt(self.powerspec_subharm) * sub.df[:, None, None]
+
+        def c64(a):
+            return torch.view_as_real(torch.from_numpy(numpy.ascontiguousarray(a, dtype=numpy.complex64))).to(dev)
+        win = phasor[:, lo:lo + P]
+        self._d['subharm'] = {'weight': torch.from_numpy(weight27.astype(numpy.float32).reshape(27)).to(dev),
+                              'ex': c64(win), 'ey': c64(win), 'mean': c64(mean27.reshape(27))}
 
     def _host(self, name):
         if name not in self._host_cache:
@@ -473,7 +519,7 @@ class Fast():
             ws = self._d['workspace'] = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         return ws
 
-    def screen_detect(self, first_pair, n_pairs, noise=None, chi=None, algo=_lib.ALGO_AUTO):
+    def screen_detect(self, first_pair, n_pairs, noise=None, chi=None, algo=_lib.ALGO_AUTO, noise_lo=None):
         """Run K2 for global pairs [first_pair, first_pair + n_pairs).  Returns two device
         tensors (results of the Re and Im realisations); complex64 when COHERENT.
         noise: optional (n_pairs, N, N) complex64 device tensor; chi: optional float32 device
@@ -484,8 +530,13 @@ class Fast():
         out_b = torch.empty(n_pairs * width, dtype=torch.float32, device=self.device)
         if n_pairs:
             nz = None if noise is None else torch.view_as_real(noise.contiguous())
+            sh = None
+            if self.subharmonics:
+                sh = dict(self._d['subharm'])
+                if noise_lo is not None:
+                    sh['noise'] = torch.view_as_real(noise_lo.contiguous())
             _lib.screen_detect(rp, self._d['weight'], self._d['U'], out_a, out_b, self._workspace(rp),
-                               chi=chi, noise=nz)
+                               chi=chi, noise=nz, subharm=sh)
         if rp.coherent:
             out_a = torch.view_as_complex(out_a.view(-1, 2))
             out_b = torch.view_as_complex(out_b.view(-1, 2))
@@ -521,6 +572,9 @@ class Fast():
             J2, N = self.Niter_per_chunk // 2, self.Npxls
             rand = funcs.generate_random_coefficients((J2, N, N)).astype(numpy.complex64)
             self._d['noise'] = torch.from_numpy(rand).to(self.device)
+            if self.subharmonics:       # drawn after the main block, like fast/fast.py:600
+                lo = funcs.generate_random_coefficients((J2, 3, 3, 3)).astype(numpy.complex64)
+                self._d['noise_lo'] = torch.from_numpy(lo.reshape(J2, 27)).to(self.device)
         return None
 
     def compute_phs_temporal(self, chunk=0):
@@ -559,8 +613,10 @@ class Fast():
             self.random_iters = self._temporal_detector(chunk)
             return self.random_iters
         ppc = self.Niter_per_chunk // 2
-        noise = self._d.get('noise') if self.rng_mode == 'numpy' else None
-        a, b = self.screen_detect(chunk * ppc, ppc, noise=noise, chi=self._d.get('chi'))
+        numpy_rng = self.rng_mode == 'numpy'
+        a, b = self.screen_detect(chunk * ppc, ppc, noise=self._d.get('noise') if numpy_rng else None,
+                                  chi=self._d.get('chi'),
+                                  noise_lo=self._d.get('noise_lo') if numpy_rng else None)
         self.random_iters = torch.cat([a, b])
         return self.random_iters
 

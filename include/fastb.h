@@ -50,7 +50,9 @@ enum { FASTB_AO_NOAO = 0, FASTB_AO_AO = 1 /* 'AO' and 'TT' */, FASTB_AO_LGSAO = 
  * All arithmetic is float64, evaluated in the reference's operation order.
  * ------------------------------------------------------------------------------------- */
 typedef struct FastbPsdParams {
-    int32_t n;                      /* grid size N (even, >= 4) */
+    int32_t n;                      /* grid size N >= 2; the zero frequency sits at index N/2
+                                       (integer division).  Main grids are even; the 3 x 3
+                                       sub-harmonic levels (fast/fast.py:835-844) use N = 3 */
     int32_t n_layers;               /* L, 1..FASTB_MAX_LAYERS */
     int32_t ao_mode;                /* FASTB_AO_* */
     int32_t alias;                  /* 1: include WFS aliasing (ignored for NOAO) */
@@ -165,6 +167,23 @@ typedef struct FastbRunParams {
     float reserved_f;
 } FastbRunParams;
 
+/* Optional sub-harmonic correction (funcs.make_phase_subharm, fast/funcs.py:225-258, added to the
+ * cropped screens at fast/fast.py:598-603).  27 plane waves: level i < 3, fy index q < 3, fx index
+ * s < 3 (flat index m = (i*3 + q)*3 + s), frequencies (s-1, q-1) * df_i, df_i = 2 pi/(3^(i+1) N dx).
+ * Per pair the complex amplitudes are noise_m * d_weight[m]; the complex screen
+ *   sum_m amp_m exp(i (x fx_m + y fy_m)) - (its mean over the full N x N grid)
+ * is added to Phi before the detector (Re -> realisation a, Im -> realisation b).
+ * Device RNG: call j < 14 with counter (j, g lo, g hi, 0x5AB4A200) yields amplitudes m = 2j
+ * (words 0,1) and m = 2j+1 (words 2,3) by the same Box-Muller as the main noise. */
+typedef struct FastbSubharm {
+    const float* d_weight;          /* 27 floats: sqrt(powerspec_subharm[i,q,s]) * df_i */
+    const float* d_noise;           /* NULL (device RNG) or n_pairs*27 complex64: the reference's
+                                       `rand_lo` (fast/fast.py:600) cast to complex64 */
+    const float* d_ex;              /* 3*n_pup complex64: exp(i x_c df_i), x_c = pupil column coords */
+    const float* d_ey;              /* 3*n_pup complex64: exp(i y_r df_i), y_r = pupil row coords */
+    const float* d_mean;            /* 27 complex64: full-grid mean of each plane wave */
+} FastbSubharm;
+
 int64_t fastb_screen_detect_workspace_bytes(const FastbRunParams* p);
 
 /* d_weight  N*N floats from fastb_psd_build / fastb_make_weight
@@ -174,11 +193,12 @@ int64_t fastb_screen_detect_workspace_bytes(const FastbRunParams* p);
  *           pair-major: the reference's `rand` array (fast/fast.py:593) cast to complex64
  * d_out_a   results of the Re realisations, element (g - first_pair) [x2 floats if coherent]
  * d_out_b   results of the Im realisations, same indexing
+ * sh        NULL, or the sub-harmonic term (SUBHARM=True)
  */
 int fastb_screen_detect(const FastbRunParams* p, const float* d_weight, const float* d_U,
-                        const float* d_chi, const float* d_noise, float* d_out_a,
-                        float* d_out_b, void* d_workspace, int64_t workspace_bytes,
-                        void* stream);
+                        const float* d_chi, const float* d_noise, const FastbSubharm* sh,
+                        float* d_out_a, float* d_out_b, void* d_workspace,
+                        int64_t workspace_bytes, void* stream);
 
 /* Debug / verification aid: materialise the device-RNG noise tile of pair g (N*N complex64)
  * and the chi normals of realisations [first, first+count).  Either output may be NULL. */

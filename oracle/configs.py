@@ -38,9 +38,11 @@ def c1(seed=1):
     return _mk(SEED=seed)
 
 
-def c1prime(niter=100, nchunks=10, seed=1):
+def c1prime(niter=100, nchunks=10, seed=1, **kw):
     """Config 1 with TEMPORAL off (test/tests_pytest.py:56-59): N auto -> 164."""
-    return _mk(TEMPORAL=False, NITER=niter, NCHUNKS=nchunks, SEED=seed)
+    d = dict(TEMPORAL=False, NITER=niter, NCHUNKS=nchunks, SEED=seed)
+    d.update(kw)
+    return _mk(**d)
 
 
 def c2(niter=100000, nchunks=1, seed=1):

@@ -799,3 +799,122 @@ def run_mc_temporal(init, rng, screens_hook=None):
         out[c] = detector(phs, U, chi[c * J:(c + 1) * J], coherent)
         interp = interp + shifts[:, :, -1, None, None]
     return out.flatten(), chi, phs
+
+
+# --------------------------------------------------------------------------------------
+# Sub-harmonics (Lane et al. style low-frequency correction): fast/fast.py:494-531, 598-603,
+# 835-844; fast/funcs.py:225-258.  Three levels p = 1..3 of 3 x 3 frequencies spaced
+# 2 pi / (3^p N dx); the residual PSD is evaluated on them with the same terms as the main grid.
+# --------------------------------------------------------------------------------------
+def subharm_axes(N, dx, pmax=3):
+    """(pmax, 3) frequency axes {-1, 0, 1} * 2 pi / (3^p N dx) (fast/fast.py:835-844)."""
+    D = dx * N
+    return np.array([np.arange(-1, 2) * (2 * np.pi / (3 ** p * D)) for p in range(1, pmax + 1)])
+
+
+def subharm_psd(init):
+    """powerspec_subharm_per_layer (L, 3, 3, 3) and its layer sum, by applying the main-grid
+    terms to each 3 x 3 level (fast/fast.py:494-523)."""
+    p, atm = init['params'], init['atm']
+    axes = subharm_axes(init['N'], init['dx'])
+    h, cn2, wind = atm['h'], atm['cn2'], atm['wind_vector']
+    L = len(h)
+    mode_name = p['AO_MODE']
+    zmax, modal, mmult = p['ZMAX'], p['MODAL'], p['MODAL_MULT']
+    if mode_name == 'TT':
+        zmax, modal, mmult = 3, True, 1
+    k = init['k']
+    out = np.zeros((L, 3, 3, 3))
+    for i, ax in enumerate(axes):
+        fx, fy = np.meshgrid(ax, ax)
+        fabs = np.sqrt(fx ** 2 + fy ** 2)
+        mask = lf_mask(fx, fy, p['DSUBAP'], modal=modal, modal_mult=mmult, Zmax=zmax, D=p['D_GROUND'])
+        turb = von_karman(fabs, cn2, p['L0'], p['l0'])
+        G = g_ao(fx, fy, mask, mode_name, h, wind, atm['dtheta'], p['TLOOP'], p['TEXP'], D=p['D_GROUND'])
+        if p['ALIAS'] and mode_name != 'NOAO':
+            alias = alias_psd(ax, ax, p['DSUBAP'], cn2, mask, wind, p['TEXP'], p['L0'], p['l0'])
+        else:
+            alias = 0.
+        if p['NOISE'] > 0 and mode_name != 'NOAO':
+            noise = noise_psd(fx, fy, p['DSUBAP'], p['NOISE'], mask)
+        else:
+            noise = 0.
+        out[:, i] = 2 * np.pi * k ** 2 * (turb * G + alias) + noise / L
+    return out, out.sum(0), axes
+
+
+def subharm_screens(noise_lo, W_sh, axes, N, dx):
+    """make_phase_subharm(double=True) (fast/funcs.py:225-258): noise_lo (J/2, 3, 3, 3) complex
+    -> (J, N, N): sum of the 27 plane waves, full-grid mean removed per complex screen,
+    Re stacked over Im."""
+    D = dx * N
+    coords = np.arange(-D / 2, D / 2, dx)[:N]
+    x, y = np.meshgrid(coords, coords)
+    acc = np.zeros((noise_lo.shape[0], N, N), dtype=complex)
+    for i in range(axes.shape[0]):
+        df_lo = axes[i, 1] - axes[i, 0]
+        fx_lo, fy_lo = np.meshgrid(axes[i], axes[i])
+        amp = noise_lo[:, i] * np.sqrt(W_sh[i]) * df_lo                      # (J/2, 3, 3)
+        modes = np.exp(1j * (x[None, None] * fx_lo[..., None, None] + y[None, None] * fy_lo[..., None, None]))
+        acc = acc + np.einsum('pqs,qsrc->prc', amp, modes)
+    acc = acc - acc.mean((1, 2))[:, None, None]
+    return np.vstack([acc.real, acc.imag])
+
+
+def run_mc_subharm(init, rng):
+    """Fast.run() with SUBHARM=True (fast/fast.py:589-605): per chunk the main noise block is
+    drawn first, then the (J/2, 3, 3, 3) sub-harmonic block.  Returns (_r, last chunk phs)."""
+    p = init['params']
+    niter, nch = p['NITER'], p['NCHUNKS']
+    J = niter // nch
+    N, dx, lo, hi = init['N'], init['dx'], init['lo'], init['hi']
+    _, W_sh, axes = subharm_psd(init)
+    U = init['pupil'] * init['pupil_mode']
+    chi = draw_logamp(rng, niter, init['logamp_var'])
+    out = np.zeros((nch, J), dtype=complex if p['COHERENT'] else float)
+    phs = None
+    for c in range(nch):
+        noise = draw_complex(rng, (J // 2, N, N))
+        phs = screens_from_noise(noise, init['powerspec'], init['df'], lo, hi)
+        noise_lo = draw_complex(rng, (J // 2, 3, 3, 3))
+        phs = phs + subharm_screens(noise_lo, W_sh, axes, N, dx)[:, lo:hi, :][:, :, lo:hi]
+        out[c] = detector(phs, U, chi[c * J:(c + 1) * J], bool(p['COHERENT']))
+    return out.flatten(), phs
+
+
+STREAM_SUBHARM = 0x5AB4A200
+
+
+def device_subharm_noise(seed, pair):
+    """(3, 3, 3) complex unit normals the CUDA generator uses for the sub-harmonics of global
+    pair `pair`: call j < 14, counter (j, pair lo, pair hi, STREAM_SUBHARM) -> flat amplitudes
+    2j (words 0,1) and 2j+1 (words 2,3), flat index m = (level*3 + q)*3 + s.  (include/fastb.h)"""
+    j = np.arange(14, dtype=np.uint64)
+    w = philox4x32_10(j, np.uint64(pair & 0xFFFFFFFF), np.uint64((pair >> 32) & 0xFFFFFFFF),
+                      np.uint64(STREAM_SUBHARM), seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    re0, im0 = box_muller(w[0], w[1])
+    re1, im1 = box_muller(w[2], w[3])
+    flat = np.empty(28, dtype=complex)
+    flat[0::2] = re0 + 1j * im0
+    flat[1::2] = re1 + 1j * im1
+    return flat[:27].reshape(3, 3, 3)
+
+
+def run_mc_device_rng_subharm(init, seed, n_pairs, pairs_per_chunk):
+    """run_mc_device_rng with the sub-harmonic term (device noise restated)."""
+    p = init['params']
+    coherent = bool(p['COHERENT'])
+    N, dx, lo, hi = init['N'], init['dx'], init['lo'], init['hi']
+    _, W_sh, axes = subharm_psd(init)
+    U = init['pupil'] * init['pupil_mode']
+    chi_all = math.sqrt(init['logamp_var']) * device_chi_normals(seed, 0, 2 * n_pairs)
+    out = np.zeros(2 * n_pairs, dtype=complex if coherent else float)
+    for g in range(n_pairs):
+        chunk, pp = divmod(g, pairs_per_chunk)
+        i_re = chunk * 2 * pairs_per_chunk + pp
+        i_im = i_re + pairs_per_chunk
+        phs = screens_from_noise(device_noise_pair(seed, g, N)[None], init['powerspec'], init['df'], lo, hi)
+        phs = phs + subharm_screens(device_subharm_noise(seed, g)[None], W_sh, axes, N, dx)[:, lo:hi, :][:, :, lo:hi]
+        r = detector(phs, U, chi_all[[i_re, i_im]], coherent)
+        out[i_re], out[i_im] = r[0], r[1]
+    return out

@@ -45,6 +45,10 @@ CASES = {
     'c5':            ('c5', {'niter': 2}, 'sub'),
     # TEMPORAL frozen-flow path (fast/fast.py:607-637): config 1 verbatim, and a 64x64 variant
     'c1_temporal':   ('c1', {}, 'temporal'),
+    # sub-harmonics (fast/funcs.py:225-258, fast/fast.py:494-531,598-603)
+    'mini_subharm':  ('mini', {'SUBHARM': True}, 'subharm'),
+    'mini_subharm_noao': ('mini', {'SUBHARM': True, 'AO_MODE': 'NOAO', 'L0': 25.0}, 'subharm'),
+    'c1prime_subharm': ('c1prime', {'niter': 8, 'nchunks': 2, 'SUBHARM': True}, 'subharm'),
     'mini_temporal': ('mini', {'TEMPORAL': True, 'NITER': 60, 'NCHUNKS': 3, 'DT': 0.002, 'COHERENT': True},
                       'temporal'),
 }
@@ -102,6 +106,13 @@ def run_case(name):
         d['phs_last_all'] = sim.phs.copy()
         d['powerspec'] = sim.powerspec
         d['logamp_powerspec'] = sim.logamp_powerspec
+    if level == 'subharm':
+        d['powerspec_subharm'] = sim.powerspec_subharm
+        d['powerspec_subharm_per_layer'] = np.asarray(sim.powerspec_subharm_per_layer)
+        d['phs_var_subharm'] = sim.phs_var_subharm
+        d['powerspec'] = sim.powerspec
+        d['logamp_powerspec'] = sim.logamp_powerspec
+        d['phs_last_all'] = sim.phs.copy()
     for s in SCALARS:
         d[s] = np.float64(getattr(sim, s))
     N = sim.Npxls

@@ -227,3 +227,33 @@ def test_temporal_device_rng_screens_match_oracle(fast):
     # same seed -> same time series; different seed -> different
     np.testing.assert_array_equal(fast.Fast(dict(p, SEED=31)).run()._r, res._r)
     assert not np.array_equal(fast.Fast(dict(p, SEED=32)).run()._r, res._r)
+
+
+# ---------------------------------------------------------------------------------------------
+# sub-harmonics (SUBHARM=True)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('name', ['mini_subharm', 'mini_subharm_noao', 'c1prime_subharm'])
+def test_subharm_run_with_reference_noise_matches_reference(fast, name):
+    g, p = load_golden(name)
+    sim = fast.Fast(dict(p, RNG='numpy'))
+    check_scalars(sim, g)
+    assert rel(sim.powerspec_subharm, g['powerspec_subharm']) < 1e-9
+    assert rel(sim.powerspec_subharm_per_layer, g['powerspec_subharm_per_layer']) < 1e-9
+    np.testing.assert_allclose(sim.phs_var_subharm, g['phs_var_subharm'], rtol=1e-9)
+    res = sim.run()
+    assert worst_rel_per_item(res._r, g['r']) < RTOL_R
+
+
+@pytest.mark.parametrize('name', ['mini_subharm', 'c1prime_subharm'])
+def test_subharm_device_rng_matches_oracle(fast, name):
+    g, p = load_golden(name)
+    sim = fast.Fast(dict(p, NITER=12, NCHUNKS=2, SEED=41))
+    got = sim.run()._r
+    want = fo.run_mc_device_rng_subharm(fo.build(p), 41, 6, 3)
+    assert np.max(np.abs(got - want) / np.abs(want)) < 5e-4
+    # radix and direct paths agree with the sub-harmonic term as well
+    if sim.Npxls == 64:
+        a1, b1 = sim.screen_detect(0, 4, algo=fast._lib.ALGO_RADIX)
+        a2, b2 = sim.screen_detect(0, 4, algo=fast._lib.ALGO_DIRECT)
+        np.testing.assert_allclose(a1.cpu().numpy(), a2.cpu().numpy(), rtol=1e-4)
+        np.testing.assert_allclose(b1.cpu().numpy(), b2.cpu().numpy(), rtol=1e-4)

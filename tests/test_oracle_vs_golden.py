@@ -169,3 +169,18 @@ def test_bilinear_matches_scipy_spline_including_clamp():
     x = np.sort(rng.uniform(0, 12, 9))
     y = np.sort(rng.uniform(0, 12, 7))
     np.testing.assert_allclose(fo.bilinear_clamped(scr, x, y), s(x, y), rtol=1e-12, atol=1e-13)
+
+
+@pytest.mark.parametrize('name', ['mini_subharm', 'mini_subharm_noao', 'c1prime_subharm'])
+def test_subharmonics(name):
+    g, p = load_golden(name)
+    init = fo.build(p)
+    check_init(g, init, ['powerspec', 'logamp_powerspec'])
+    per_layer, W_sh, axes = fo.subharm_psd(init)
+    assert rel(per_layer, g['powerspec_subharm_per_layer']) < 1e-12
+    assert rel(W_sh, g['powerspec_subharm']) < 1e-12
+    df_lo = axes[:, 1] - axes[:, 0]
+    np.testing.assert_allclose(per_layer.sum((-1, -2)) * df_lo ** 2, g['phs_var_subharm'], rtol=1e-12)
+    r, phs = fo.run_mc_subharm(init, np.random.default_rng(p['SEED']))
+    assert rel(phs, g['phs_last_all']) < 1e-10
+    assert rel(r, g['r']) < 1e-10
