@@ -166,6 +166,49 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------- cuFFT comparator
+def cufft_comparator(sim, n_real, steps, batch_pairs=256):
+    """Library-built pipeline for the same work, timed in the same process as an FFT
+    comparator (BASELINE.json north_star): cuRAND Philox normals (torch.randn) -> x weight ->
+    cuFFT batched 2-D C2C (torch.fft.ifft2) -> crop -> exp / sum reductions (torch).  Not the
+    product path; it materialises full N x N screens in HBM like the reference does."""
+    import torch
+    dev = sim.device
+    N, P, lo = sim.Npxls, sim.Npxls_pup, sim._lo
+    w_abs = sim._d['weight'].abs().to(torch.complex64) * (N * N)       # ifft2 normalises by 1/N^2
+    w_shift = torch.fft.ifftshift(w_abs)                               # centred spectrum -> FFT order
+    U = sim._d['U']
+    inv = 1.0 / sim._u_sum
+    sig = float(sim.logamp_var) ** 0.5
+    n_pairs = n_real // 2
+
+    def one_step():
+        acc = []
+        for p0 in range(0, n_pairs, batch_pairs):
+            b = min(batch_pairs, n_pairs - p0)
+            z = torch.randn((b, N, N, 2), device=dev)
+            s = torch.view_as_complex(z) * w_shift
+            scr = torch.fft.fftshift(torch.fft.ifft2(s), dim=(-1, -2))[:, lo:lo + P, lo:lo + P]
+            chi = sig * torch.randn((2, b), device=dev)
+            za = (U * torch.exp(1j * scr.real)).sum((1, 2)) * inv * torch.exp(chi[0])
+            zb = (U * torch.exp(1j * scr.imag)).sum((1, 2)) * inv * torch.exp(chi[1])
+            acc.append(torch.cat([za.abs() ** 2, zb.abs() ** 2]))
+        return torch.cat(acc)
+
+    r = one_step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        r = one_step()
+    e1.record()
+    e1.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"kind": "cuRAND (torch.randn) + cuFFT (torch.fft.ifft2, batched C2C) + torch reductions, "
+                    "full N x N screens in HBM", "value": n_real / (ms * 1e-3), "unit": UNIT,
+            "ms_per_step": ms, "mean_r": float(r.mean())}
+
+
 # ------------------------------------------------------------------------- GPU
 def run_ours(args):
     import torch
@@ -287,6 +330,9 @@ def run_ours(args):
                 traffic = json.load(open(tpath)).get(args.workload)
             except Exception:
                 traffic = None
+        comparator = None
+        if world == 1 and not args.no_comparator and not coherent:
+            comparator = cufft_comparator(sim, n_real, max(2, args.steps // 4))
         cpu = None
         if world == 1 and not args.no_cpu:
             n_cpu = {'c2': 2000, 'c4': 500, 'c5': 120}[args.workload]
@@ -308,6 +354,7 @@ def run_ours(args):
                              "algorithmic_bytes_per_realization": b_alg,
                              "realizations_per_launch": n_real},
                 "cpu_baseline": cpu,
+                "comparator": comparator,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": int(launches),
                 "clocks": sampler.summary(),
@@ -325,6 +372,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--no-comparator', action='store_true', help='skip the cuFFT comparator leg')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'ours':
         args.warmup = 3

@@ -257,3 +257,19 @@ def test_subharm_device_rng_matches_oracle(fast, name):
         a2, b2 = sim.screen_detect(0, 4, algo=fast._lib.ALGO_DIRECT)
         np.testing.assert_allclose(a1.cpu().numpy(), a2.cpu().numpy(), rtol=1e-4)
         np.testing.assert_allclose(b1.cpu().numpy(), b2.cpu().numpy(), rtol=1e-4)
+
+
+def test_elevation_sweep_matches_individual_runs(fast):
+    """C3: the batched sweep gives exactly what running each sample on its own gives, and the
+    physics is monotonic in elevation (lower elevation -> deeper fades; SURVEY 8c iv)."""
+    from fast_b200 import configs, sweep
+    els = [10.0, 30.0, 60.0, 85.0]
+    ps = [configs.c3_elevation(e, niter=2000, nchunks=2, seed=100 + i) for i, e in enumerate(els)]
+    sims = sweep.build_sims([dict(p) for p in ps])
+    res = sweep.run_sweep(sims)
+    for p, r in zip(ps, res):
+        solo = fast.Fast(dict(p)).run()
+        np.testing.assert_array_equal(r._r, solo._r)
+    means = [r.dB_rel.mean() for r in res]
+    assert means[0] < means[1] < means[2]
+    assert sims[0].L > sims[-1].L and sims[0].h[0] > sims[-1].h[0]
