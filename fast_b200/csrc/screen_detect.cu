@@ -261,6 +261,12 @@ screen_detect_radix(const __grid_constant__ RunArgs a) {
             const bool rows = it < n1;
             if (it == n1) __syncthreads();            // every row of T is stored before a column is read
             const int line = (rows ? it : it - n1) * LPB + ln;      // r' (pass 1) or c (pass 2)
+            if (S1 <= 32 && !rows) {
+                // last column iteration: warps whose lines all lie beyond the crop have nothing
+                // to do (a line lives inside one warp, so no barrier is skipped)
+                constexpr int kLinesPerWarp = S1 <= 32 ? 32 / S1 : 1;
+                if (line - (ln % kLinesPerWarp) >= P) continue;
+            }
             float2 v[16];
             if (rows) {
                 const float* wrow = a.weight + (size_t)line * N;
