@@ -54,23 +54,53 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
     return make_uint4(c0, c1, c2, c3);
 }
 
-// Box-Muller on two Philox words, scaled by w: radius from wa (argument 1 - (wa>>9) 2^-23 in
-// (0, 1]), angle 2 pi (wb>>9) 2^-23.  The mantissa trick builds 1+u in [1, 2) without an
-// int->float conversion; sin/cos are 2 pi-periodic so 2 pi (1+u) is used directly.
+// Box-Muller from two 23-bit mantissa fields, scaled by w: radius argument 1 - mr 2^-23 in (0, 1],
+// angle 2 pi ma 2^-23.  The mantissa trick builds 1+u in [1, 2) without an int->float conversion;
+// sin/cos are 2 pi-periodic so 2 pi (1+u) is used directly.
 // 4 MUFU (lg2, sqrt, sin, cos) + 5 FMUL + 1 FADD per complex sample.
-__device__ __forceinline__ float2 weighted_normal(uint32_t wa, uint32_t wb, float w) {
-    const float u1 = 2.0f - __uint_as_float(0x3f800000u | (wa >> 9));
+__device__ __forceinline__ float2 weighted_normal_m(uint32_t mr, uint32_t ma, float w) {
+    const float u1 = 2.0f - __uint_as_float(0x3f800000u | mr);
     float rad;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(-1.3862943611198906f * __log2f(u1)));
     rad *= w;
-    const float ang = 6.283185307179586f * __uint_as_float(0x3f800000u | (wb >> 9));
+    const float ang = 6.283185307179586f * __uint_as_float(0x3f800000u | ma);
     float s, c;
     __sincosf(ang, &s, &c);
     return make_float2(rad * c, rad * s);
 }
 
+// top 23 bits of each word (used by the chi and sub-harmonic streams)
 __device__ __forceinline__ float2 box_muller(uint32_t wa, uint32_t wb) {
-    return weighted_normal(wa, wb, 1.0f);
+    return weighted_normal_m(wa >> 9, wb >> 9, 1.0f);
+}
+
+// ---- phase-noise stream ------------------------------------------------------------------
+// Noise block b = r * S + t (S = ceil(N/16)) holds the 16 cells (r, t + S m), m < 16, of pair g.
+// It is fed by SIX Philox calls q < 6 with counter (b, g lo, g hi, kStreamNoise + q): 24 words
+// W[4q + j].  Each group of three words G < 8 (W[3G], W[3G+1], W[3G+2]) yields four 23-bit
+// fields: the top 23 bits of each word, plus one field mixed from their low 9 bits, so that
+// 24 words feed 32 uniforms = 16 Box-Muller pairs (8 calls would otherwise be needed):
+//   cell m = 2G   : radius W[3G]   >> 9, angle W[3G+1] >> 9
+//   cell m = 2G+1 : radius W[3G+2] >> 9, angle (W[3G]&511) << 14 | (W[3G+1]&511) << 5 | (W[3G+2] >> 4)&31
+__device__ __forceinline__ void noise_block_fields(uint32_t block, unsigned long long g, uint32_t k0,
+                                                   uint32_t k1, uint32_t (&mr)[16], uint32_t (&ma)[16]) {
+    uint32_t W[24];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+        const uint4 w = philox4x32_10(block, (uint32_t)g, (uint32_t)(g >> 32), kStreamNoise + q, k0, k1);
+        W[4 * q] = w.x;
+        W[4 * q + 1] = w.y;
+        W[4 * q + 2] = w.z;
+        W[4 * q + 3] = w.w;
+    }
+#pragma unroll
+    for (int G = 0; G < 8; ++G) {
+        const uint32_t a = W[3 * G], b = W[3 * G + 1], c = W[3 * G + 2];
+        mr[2 * G] = a >> 9;
+        ma[2 * G] = b >> 9;
+        mr[2 * G + 1] = c >> 9;
+        ma[2 * G + 1] = ((a & 0x1FFu) << 14) | ((b & 0x1FFu) << 5) | ((c >> 4) & 0x1Fu);
+    }
 }
 
 // standard normal n_i used for the log-amplitude of global realisation index i

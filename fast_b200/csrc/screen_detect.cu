@@ -271,14 +271,10 @@ screen_detect_radix(const __grid_constant__ RunArgs a) {
             if (rows) {
                 const float* wrow = a.weight + (size_t)line * N;
                 if (RNG) {
+                    uint32_t mr[16], ma[16];
+                    noise_block_fields((uint32_t)(line * S1 + u), g, k0, k1, mr, ma);
 #pragma unroll
-                    for (int m = 0; m < 8; ++m) {
-                        const int j = u + S1 * m;
-                        const uint4 w = philox4x32_10((uint32_t)(line * (N / 2) + j), (uint32_t)g,
-                                                      (uint32_t)(g >> 32), kStreamNoise, k0, k1);
-                        v[m] = weighted_normal(w.x, w.y, __ldg(wrow + j));
-                        v[m + 8] = weighted_normal(w.z, w.w, __ldg(wrow + j + N / 2));
-                    }
+                    for (int m = 0; m < 16; ++m) v[m] = weighted_normal_m(mr[m], ma[m], __ldg(wrow + u + S1 * m));
                 } else {
                     const float2* nrow = a.noise + ((size_t)pair * N + line) * N;
 #pragma unroll
@@ -348,7 +344,6 @@ __global__ void __launch_bounds__(kThreads) screen_detect_direct(const __grid_co
 
     float2* T = a.scratch + (size_t)blockIdx.x * N * P;
     const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
-    const int half = N / 2;
 
     for (long long pair = blockIdx.x; pair < a.n_pairs; pair += gridDim.x) {
         const unsigned long long g = (unsigned long long)(a.first_pair + pair);
@@ -356,14 +351,16 @@ __global__ void __launch_bounds__(kThreads) screen_detect_direct(const __grid_co
         for (int row0 = 0; row0 < N; row0 += R) {
             const int nr = min(R, N - row0);
             if (RNG) {
-                for (int idx = tid; idx < nr * half; idx += kThreads) {
-                    const int rl = idx / half, j = idx % half, r = row0 + rl;
-                    const uint4 w = philox4x32_10((uint32_t)(r * half + j), (uint32_t)g,
-                                                  (uint32_t)(g >> 32), kStreamNoise, k0, k1);
-                    const float2 n0 = box_muller(w.x, w.y), n1 = box_muller(w.z, w.w);
-                    const float w0 = a.weight[(size_t)r * N + j], w1 = a.weight[(size_t)r * N + j + half];
-                    rows[rl * N + j] = make_float2(n0.x * w0, n0.y * w0);
-                    rows[rl * N + j + half] = make_float2(n1.x * w1, n1.y * w1);
+                const int S = (N + 15) / 16;
+                for (int idx = tid; idx < nr * S; idx += kThreads) {
+                    const int rl = idx / S, t = idx % S, r = row0 + rl;
+                    uint32_t mr[16], ma[16];
+                    noise_block_fields((uint32_t)(r * S + t), g, k0, k1, mr, ma);
+#pragma unroll
+                    for (int m = 0; m < 16; ++m) {
+                        const int j = t + S * m;
+                        if (j < N) rows[rl * N + j] = weighted_normal_m(mr[m], ma[m], a.weight[(size_t)r * N + j]);
+                    }
                 }
             } else {
                 for (int idx = tid; idx < nr * N; idx += kThreads) {
@@ -429,13 +426,16 @@ __global__ void transpose_u_kernel(const float* __restrict__ U, int P, float* __
 __global__ void rng_dump_kernel(unsigned long long seed, unsigned long long g, int N, float2* tile,
                                 long long chi_first, long long chi_count, float* chi) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int half = N / 2;
-    if (tile && i < (long long)N * half) {
-        const int r = (int)(i / half), j = (int)(i % half);
-        const uint4 w = philox4x32_10((uint32_t)(r * half + j), (uint32_t)g, (uint32_t)(g >> 32),
-                                      kStreamNoise, (uint32_t)seed, (uint32_t)(seed >> 32));
-        tile[(size_t)r * N + j] = box_muller(w.x, w.y);
-        tile[(size_t)r * N + j + half] = box_muller(w.z, w.w);
+    const int S = (N + 15) / 16;
+    if (tile && i < (long long)N * S) {
+        const int r = (int)(i / S), t = (int)(i % S);
+        uint32_t mr[16], ma[16];
+        noise_block_fields((uint32_t)(r * S + t), g, (uint32_t)seed, (uint32_t)(seed >> 32), mr, ma);
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            const int j = t + S * m;
+            if (j < N) tile[(size_t)r * N + j] = weighted_normal_m(mr[m], ma[m], 1.0f);
+        }
     }
     if (chi && i < chi_count) chi[i] = chi_normal(seed, (uint64_t)(chi_first + i));
 }
@@ -620,7 +620,7 @@ extern "C" int fastb_rng_dump(uint64_t seed, int64_t pair, int32_t n, float* d_n
                               int64_t chi_first, int64_t chi_count, float* d_chi_normals, void* stream) {
     FASTB_REQUIRE(n >= 2 && (n % 2) == 0, "fastb_rng_dump: n must be even");
     FASTB_REQUIRE(pair >= 0 && chi_first >= 0 && chi_count >= 0, "fastb_rng_dump: negative index");
-    long long work = d_noise_tile ? (long long)n * (n / 2) : 0;
+    long long work = d_noise_tile ? (long long)n * ((n + 15) / 16) : 0;
     if (d_chi_normals && chi_count > work) work = chi_count;
     if (work == 0) return FASTB_OK;
     rng_dump_kernel<<<(unsigned)((work + 255) / 256), 256, 0, (cudaStream_t)stream>>>(

@@ -27,16 +27,20 @@ __global__ void __launch_bounds__(kThreads) screens_rows_kernel(int n, unsigned 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* tw = reinterpret_cast<float2*>(smem_raw);
     float2* row = tw + n;
-    const int r = blockIdx.x, l = blockIdx.y, tid = threadIdx.x, half = n / 2;
+    const int r = blockIdx.x, l = blockIdx.y, tid = threadIdx.x;
     const size_t base = ((size_t)l * n + r) * n;
     for (int j = tid; j < n; j += kThreads) tw[j] = tw_g[j];
     if (RNG) {
         const unsigned long long g = FASTB_LAYER_PAIR_BASE + (unsigned long long)l;
-        for (int j = tid; j < half; j += kThreads) {
-            const uint4 w = philox4x32_10((uint32_t)(r * half + j), (uint32_t)g, (uint32_t)(g >> 32),
-                                          kStreamNoise, (uint32_t)seed, (uint32_t)(seed >> 32));
-            row[j] = weighted_normal(w.x, w.y, weight[base + j]);
-            row[j + half] = weighted_normal(w.z, w.w, weight[base + j + half]);
+        const int S = (n + 15) / 16;
+        for (int t = tid; t < S; t += kThreads) {
+            uint32_t mr[16], ma[16];
+            noise_block_fields((uint32_t)(r * S + t), g, (uint32_t)seed, (uint32_t)(seed >> 32), mr, ma);
+#pragma unroll
+            for (int m = 0; m < 16; ++m) {
+                const int j = t + S * m;
+                if (j < n) row[j] = weighted_normal_m(mr[m], ma[m], weight[base + j]);
+            }
         }
     } else {
         for (int j = tid; j < n; j += kThreads) {

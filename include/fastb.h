@@ -136,13 +136,17 @@ int64_t fastb_pupil_filter_workspace_bytes(int32_t n);
  *   i_a = (g / ppc) * 2 ppc + g % ppc   and the Im realisation  i_b = i_a + ppc.
  * chi is indexed by that global index.
  *
- * Device RNG (d_noise == NULL): Philox4x32-10, key = (seed lo, seed hi).  Noise cell call
- * q = r*(N/2) + j (j < N/2) uses counter (q, g lo, g hi, 0x5CE7E000) and yields cells (r, j)
- * from words (0,1) and (r, j+N/2) from words (2,3) by Box-Muller:
- *   radius = sqrt(-2 ln(1 - (w_even >> 9) 2^-23)),  angle = 2 pi (w_odd >> 9) 2^-23,
+ * Device RNG (d_noise == NULL): Philox4x32-10, key = (seed lo, seed hi).  Noise block
+ * b = r*S + t, S = ceil(N/16), holds the 16 cells (r, t + S m), m < 16.  It is fed by six calls
+ * q < 6 with counter (b, g lo, g hi, 0x5CE7E000 + q): 24 words W[4q+j].  Word triple G < 8
+ * (W[3G], W[3G+1], W[3G+2]) gives four 23-bit fields -- the top 23 bits of each word and one
+ * field mixed from their low 9 bits -- so 24 words feed 16 Box-Muller pairs:
+ *   cell m = 2G  : radius field W[3G] >> 9,   angle field W[3G+1] >> 9
+ *   cell m = 2G+1: radius field W[3G+2] >> 9, angle field (W[3G]&511)<<14 | (W[3G+1]&511)<<5 | (W[3G+2]>>4)&31
+ *   radius = sqrt(-2 ln(1 - field 2^-23)),  angle = 2 pi field 2^-23,
  *   Re = radius cos(angle), Im = radius sin(angle).
  * chi_i = sigma_chi * n_i, n_i = normal (i % 4) of call i / 4 with counter
- * (i/4 lo, i/4 hi, 0, 0x10CA3900).  Results depend only on (seed, g), never on the launch
+ * (i/4 lo, i/4 hi, 0, 0x10CA3900), Box-Muller on the top 23 bits of word pairs (0,1), (2,3).  Results depend only on (seed, g), never on the launch
  * geometry or the number of GPUs.
  * ------------------------------------------------------------------------------------- */
 enum {

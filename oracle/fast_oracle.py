@@ -604,23 +604,35 @@ def box_muller(ua, ub):
     return r * np.cos(t), r * np.sin(t)
 
 
+def _bm_fields(mr, ma):
+    """Box-Muller on 23-bit fields: radius argument 1 - mr 2^-23, angle 2 pi ma 2^-23."""
+    r = np.sqrt(-2.0 * np.log(1.0 - mr.astype(np.float64) * 2.0 ** -23))
+    t = 2.0 * np.pi * ma.astype(np.float64) * 2.0 ** -23
+    return r * np.cos(t) + 1j * r * np.sin(t)
+
+
 def device_noise_pair(seed, pair, N):
-    """The complex white-noise tile the CUDA generator produces for global pair index `pair`:
-    Philox call q = r*(N/2) + hcol, counter (q, pair_lo, pair_hi, STREAM_NOISE), key
-    (seed_lo, seed_hi) yields cells (r, hcol) [words 0,1] and (r, hcol + N/2) [words 2,3];
-    word 0/2 -> radius, word 1/3 -> angle; Re = r cos, Im = r sin.  (include/fastb.h)"""
-    half = N // 2
-    q = (np.arange(N, dtype=np.uint64)[:, None] * np.uint64(half)
-         + np.arange(half, dtype=np.uint64)[None, :])
-    w = philox4x32_10(q & np.uint64(0xFFFFFFFF), np.uint64(pair & 0xFFFFFFFF),
-                      np.uint64((pair >> 32) & 0xFFFFFFFF), np.uint64(STREAM_NOISE),
-                      seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
-    re0, im0 = box_muller(w[0], w[1])
-    re1, im1 = box_muller(w[2], w[3])
-    out = np.empty((N, N), dtype=complex)
-    out[:, :half] = re0 + 1j * im0
-    out[:, half:] = re1 + 1j * im1
-    return out
+    """The complex white-noise tile the CUDA generator produces for global pair index `pair`
+    (contract: include/fastb.h).  Noise block b = r*S + t, S = ceil(N/16), holds cells
+    (r, t + S m), m < 16; six Philox calls q with counter (b, pair lo, pair hi, STREAM_NOISE + q)
+    give 24 words; each word triple feeds two Box-Muller pairs (top 23 bits of each word, plus
+    one field mixed from the three low 9-bit remainders)."""
+    S = (N + 15) // 16
+    b = (np.arange(N, dtype=np.uint64)[:, None] * np.uint64(S) + np.arange(S, dtype=np.uint64)[None, :])
+    W = []
+    for q in range(6):
+        w = philox4x32_10(b, np.uint64(pair & 0xFFFFFFFF), np.uint64((pair >> 32) & 0xFFFFFFFF),
+                          np.uint64(STREAM_NOISE + q), seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+        W.extend(w)
+    out = np.zeros((N, S * 16), dtype=complex)
+    t = np.arange(S)
+    nine, five = np.uint32(0x1FF), np.uint32(0x1F)
+    for G in range(8):
+        a, bb, c = W[3 * G], W[3 * G + 1], W[3 * G + 2]
+        mix = ((a & nine) << np.uint32(14)) | ((bb & nine) << np.uint32(5)) | ((c >> np.uint32(4)) & five)
+        out[:, t + S * (2 * G)] = _bm_fields(a >> np.uint32(9), bb >> np.uint32(9))
+        out[:, t + S * (2 * G + 1)] = _bm_fields(c >> np.uint32(9), mix)
+    return out[:, :N]
 
 
 def device_chi_normals(seed, first, count):
