@@ -21,7 +21,7 @@ COMMON = ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC', '--expt-relax
 SOURCES = {
     'api.cu': [],
     'psd_build.cu': ['-fmad=false'],
-    'screen_detect.cu': ['-Xptxas', '-v'],
+    'screen_detect.cu': ['-Xptxas', '-v'] + (['-DFASTB_TUNE'] if os.environ.get('FASTB_TUNE') else []),
     'stats.cu': [],
     'temporal.cu': [],
 }
@@ -35,6 +35,7 @@ def _digest():
                 h.update(f.encode())
                 h.update(fh.read())
     h.update(repr(SOURCES).encode())
+    h.update(os.environ.get('FASTB_TUNE', '').encode())
     return h.hexdigest()
 
 

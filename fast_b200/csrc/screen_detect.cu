@@ -178,31 +178,34 @@ __device__ void finish_pair(const RunArgs& a, long long pair, float (&acc)[4], f
     __syncthreads();
 }
 
+// Synchronise the S1 threads that share one line.  S1 <= 32: the line lives inside a warp.
+// S1 = 64 / 128 (N = 1024 / 2048): a named barrier per line (ids 1..LPB; 0 is __syncthreads),
+// so lines do not wait for each other.
 template <int S1>
-__device__ __forceinline__ void line_sync() {
-    if (S1 > 32) __syncthreads();
+__device__ __forceinline__ void line_sync(int ln) {
+    if (S1 > 32) asm volatile("bar.sync %0, %1;" ::"r"(ln + 1), "n"(S1) : "memory");
     else __syncwarp();
 }
 
 // run phases A..C of the line FFT on v (see fft_core.cuh); u = thread index within the line
 template <int LOG2N>
-__device__ __forceinline__ void line_fft(int u, float2 (&v)[16], const float2* twa, const float2* twb,
+__device__ __forceinline__ void line_fft(int ln, int u, float2 (&v)[16], const float2* twa, const float2* twb,
                                          float2* buf) {
     using F = LineFFT<LOG2N>;
     F::phase_a(u, v, twa, buf);
-    line_sync<F::S1>();
+    line_sync<F::S1>(ln);
     if (F::kThree) {
         F::phase_b(u, v, twb, buf);
         if (F::S2 > 1) {
-            line_sync<F::S1>();
+            line_sync<F::S1>(ln);
             F::phase_b_store(u, v, buf);
-            line_sync<F::S1>();
+            line_sync<F::S1>(ln);
             F::phase_c(u, v, buf);
         }
     } else {
         F::phase_c(u, v, buf);
     }
-    line_sync<F::S1>();          // buffer may be rewritten by the next line
+    line_sync<F::S1>(ln);        // buffer may be rewritten by the next line
 }
 
 // One loop body serves both passes (keeps the kernel inside the instruction cache): iterations
@@ -214,8 +217,8 @@ __device__ __forceinline__ void line_fft(int u, float2 (&v)[16], const float2* t
 template <int LOG2N>
 constexpr int radix_min_blocks() { return LOG2N == 9 ? 2 : 3; }
 
-template <int LOG2N, bool RNG, bool SH>
-__global__ void __launch_bounds__(kThreads, radix_min_blocks<LOG2N>())
+template <int LOG2N, bool RNG, bool SH, int MINB = radix_min_blocks<LOG2N>()>
+__global__ void __launch_bounds__(kThreads, MINB)
 screen_detect_radix(const __grid_constant__ RunArgs a) {
     using F = LineFFT<LOG2N>;
     constexpr int N = F::N, S1 = F::S1, LPB = kThreads / S1;
@@ -261,9 +264,9 @@ screen_detect_radix(const __grid_constant__ RunArgs a) {
             const bool rows = it < n1;
             if (it == n1) __syncthreads();            // every row of T is stored before a column is read
             const int line = (rows ? it : it - n1) * LPB + ln;      // r' (pass 1) or c (pass 2)
-            if (S1 <= 32 && !rows) {
+            if (!rows) {
                 // last column iteration: warps whose lines all lie beyond the crop have nothing
-                // to do (a line lives inside one warp, so no barrier is skipped)
+                // to do (line barriers involve only the threads of that line)
                 constexpr int kLinesPerWarp = S1 <= 32 ? 32 / S1 : 1;
                 if (line - (ln % kLinesPerWarp) >= P) continue;
             }
@@ -290,7 +293,7 @@ screen_detect_radix(const __grid_constant__ RunArgs a) {
 #pragma unroll
                 for (int m = 0; m < 16; ++m) v[m] = __ldcg(tcol + u + S1 * m);
             }
-            line_fft<LOG2N>(u, v, twa, twb, buf);
+            line_fft<LOG2N>(ln, u, v, twa, twb, buf);
             if (rows) {
                 float2* tb = T + ((long long)kb * N + line);  // &T[(k - lo) * N + r'] at k_off = 0
 #pragma unroll
@@ -479,6 +482,16 @@ int launch_radix(const RunArgs& args, bool rng, int max_grid, cudaStream_t st) {
     void (*kern)(RunArgs) = nullptr;
     if (sh) kern = rng ? screen_detect_radix<LOG2N, true, true> : screen_detect_radix<LOG2N, false, true>;
     else kern = rng ? screen_detect_radix<LOG2N, true, false> : screen_detect_radix<LOG2N, false, false>;
+#ifdef FASTB_TUNE
+    // tuning builds only: FASTB_MIN_BLOCKS=2|3|4 overrides the CTAs/SM register budget
+    if (rng && !sh) {
+        const char* e = getenv("FASTB_MIN_BLOCKS");
+        const int v = e ? atoi(e) : 0;
+        if (v == 2) kern = screen_detect_radix<LOG2N, true, false, 2>;
+        if (v == 3) kern = screen_detect_radix<LOG2N, true, false, 3>;
+        if (v == 4) kern = screen_detect_radix<LOG2N, true, false, 4>;
+    }
+#endif
     FASTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     FASTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                                     cudaSharedmemCarveoutMaxShared));
