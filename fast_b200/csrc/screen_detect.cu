@@ -139,6 +139,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // fixed-order reduction of the 4 accumulators over the CTA, then the per-pair epilogue
+template <int THREADS = kThreads>
 __device__ void finish_pair(const RunArgs& a, long long pair, float (&acc)[4], float* red) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -150,7 +151,7 @@ __device__ void finish_pair(const RunArgs& a, long long pair, float (&acc)[4], f
     __syncthreads();
     if (threadIdx.x == 0) {
         float t[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int w = 0; w < kThreads / 32; ++w)
+        for (int w = 0; w < THREADS / 32; ++w)
             for (int i = 0; i < 4; ++i) t[i] += red[w * 4 + i];
         const long long g = a.first_pair + pair;
         const long long chunk = g / a.ppc, pp = g % a.ppc;
@@ -212,22 +213,28 @@ __device__ __forceinline__ void line_fft(int ln, int u, float2 (&v)[16], const f
 // [0, n1) are frequency rows (noise -> FFT -> pruned store to T[c][r']), iterations [n1, n1+n2)
 // are kept columns (load T[c][:] -> FFT -> detector accumulation).  No CTA-wide barrier inside a
 // pass when a line fits in a warp (N <= 512).
-// CTAs per SM (register budget): measured on B200 (profiles/), 3 CTAs/SM (<= 80 registers, no
-// spills) is best except at N = 512, where 2 CTAs/SM with 124 registers wins.
+// CTA shape per grid size, measured on B200 (profiles/):
+//   N <= 256 : 128 threads x 4 CTAs/SM (128 registers) -- small CTAs keep the three per-pair
+//              barriers cheap and balance the 82 pupil columns over 8 lines per iteration
+//   N  = 512 : 256 threads x 2 CTAs/SM (128 registers) -- more CTAs thrash L2 with scratch
+//   N >= 1024: 256 threads x 3 CTAs/SM (80 registers)
 template <int LOG2N>
-constexpr int radix_min_blocks() { return LOG2N == 9 ? 2 : 3; }
+constexpr int radix_threads() { return LOG2N <= 8 ? 128 : 256; }
+template <int LOG2N>
+constexpr int radix_min_blocks() { return LOG2N <= 8 ? 4 : (LOG2N == 9 ? 2 : 3); }
 
-template <int LOG2N, bool RNG, bool SH, int MINB = radix_min_blocks<LOG2N>()>
-__global__ void __launch_bounds__(kThreads, MINB)
+template <int LOG2N, bool RNG, bool SH, int THREADS = radix_threads<LOG2N>(), int MINB = radix_min_blocks<LOG2N>()>
+__global__ void __launch_bounds__(THREADS, MINB)
 screen_detect_radix(const __grid_constant__ RunArgs a) {
     using F = LineFFT<LOG2N>;
-    constexpr int N = F::N, S1 = F::S1, LPB = kThreads / S1;
+    constexpr int N = F::N, S1 = F::S1, LPB = THREADS / S1;
+    static_assert(THREADS % S1 == 0 && LPB >= 1 && (S1 <= 32 || LPB <= 15), "line/barrier layout");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* twa = reinterpret_cast<float2*>(smem_raw);
     float2* twb = twa + F::kTwA;
     float2* bufs = twb + F::kTwB;
     float* red = reinterpret_cast<float*>(bufs + LPB * F::kBuf);
-    float2* sh_amp = reinterpret_cast<float2*>(red + 4 * (kThreads / 32));     // SH only
+    float2* sh_amp = reinterpret_cast<float2*>(red + 4 * (THREADS / 32));     // SH only
     float2* sh_tab = sh_amp + 28;
 
     const int tid = threadIdx.x;
@@ -235,7 +242,7 @@ screen_detect_radix(const __grid_constant__ RunArgs a) {
     float2* buf = bufs + ln * F::kBuf;
     const int P = a.n_pup, lo = a.lo;
 
-    for (int j = tid; j < F::kTwA + F::kTwB; j += kThreads) {
+    for (int j = tid; j < F::kTwA + F::kTwB; j += THREADS) {
         const int ex = j < F::kTwA ? F::twa_exponent(j) : F::twb_exponent(j - F::kTwA);
         double s, c;
         sincospi(2.0 * (double)ex / (double)N, &s, &c);
@@ -322,7 +329,7 @@ screen_detect_radix(const __grid_constant__ RunArgs a) {
                 }
             }
         }
-        finish_pair(a, pair, acc, red);
+        finish_pair<THREADS>(a, pair, acc, red);
     }
 }
 
@@ -448,11 +455,11 @@ size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 size_t sh_smem_bytes(bool sh, int n_pup) { return sh ? sizeof(float2) * (28 + (size_t)kShTab * n_pup) : 0; }
 
 template <int LOG2N>
-size_t radix_smem_bytes(bool sh, int n_pup) {
+size_t radix_smem_bytes(bool sh, int n_pup, int threads = kThreads) {
     using F = LineFFT<LOG2N>;
-    const int LPB = kThreads / F::S1;
+    const int LPB = threads / F::S1;
     return sizeof(float2) * ((size_t)F::kTwA + F::kTwB + (size_t)LPB * F::kBuf) +
-           sizeof(float) * 4 * (kThreads / 32) + sh_smem_bytes(sh, n_pup);
+           sizeof(float) * 4 * (threads / 32) + sh_smem_bytes(sh, n_pup);
 }
 
 int direct_rows(int n) {
@@ -473,30 +480,40 @@ int sm_count(int* out) {
     return FASTB_OK;
 }
 
-constexpr int kMaxCtasPerSm = 4;
+constexpr int kMaxCtasPerSm = 12;
 
 template <int LOG2N>
 int launch_radix(const RunArgs& args, bool rng, int max_grid, cudaStream_t st) {
     const bool sh = args.sh_weight != nullptr;
-    const size_t smem = radix_smem_bytes<LOG2N>(sh, args.n_pup);
+    int threads = radix_threads<LOG2N>();
     void (*kern)(RunArgs) = nullptr;
     if (sh) kern = rng ? screen_detect_radix<LOG2N, true, true> : screen_detect_radix<LOG2N, false, true>;
     else kern = rng ? screen_detect_radix<LOG2N, true, false> : screen_detect_radix<LOG2N, false, false>;
 #ifdef FASTB_TUNE
-    // tuning builds only: FASTB_MIN_BLOCKS=2|3|4 overrides the CTAs/SM register budget
+    // tuning builds only: FASTB_VARIANT selects CTA size / CTAs per SM for the bench path
     if (rng && !sh) {
-        const char* e = getenv("FASTB_MIN_BLOCKS");
+        const char* e = getenv("FASTB_VARIANT");
         const int v = e ? atoi(e) : 0;
-        if (v == 2) kern = screen_detect_radix<LOG2N, true, false, 2>;
-        if (v == 3) kern = screen_detect_radix<LOG2N, true, false, 3>;
-        if (v == 4) kern = screen_detect_radix<LOG2N, true, false, 4>;
+        if constexpr (LOG2N <= 9) {
+            if (v == 648) { kern = screen_detect_radix<LOG2N, true, false, 64, 8>; threads = 64; }
+            if (v == 6412) { kern = screen_detect_radix<LOG2N, true, false, 64, 12>; threads = 64; }
+            if (v == 5121) { kern = screen_detect_radix<LOG2N, true, false, 512, 1>; threads = 512; }
+        }
+        if constexpr (LOG2N <= 10) {
+            if (v == 1284) { kern = screen_detect_radix<LOG2N, true, false, 128, 4>; threads = 128; }
+            if (v == 1285) { kern = screen_detect_radix<LOG2N, true, false, 128, 5>; threads = 128; }
+            if (v == 1286) { kern = screen_detect_radix<LOG2N, true, false, 128, 6>; threads = 128; }
+        }
+        if (v == 2562) kern = screen_detect_radix<LOG2N, true, false, 256, 2>;
+        if (v == 2563) kern = screen_detect_radix<LOG2N, true, false, 256, 3>;
     }
 #endif
+    const size_t smem = radix_smem_bytes<LOG2N>(sh, args.n_pup, threads);
     FASTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     FASTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                                     cudaSharedmemCarveoutMaxShared));
     int per_sm = 0, sms = 0;
-    FASTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
+    FASTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
     if (per_sm < 1) {
         set_error("screen_detect_radix: kernel does not fit (smem %zu B)", smem);
         return FASTB_ERR_UNSUPPORTED;
@@ -507,7 +524,7 @@ int launch_radix(const RunArgs& args, bool rng, int max_grid, cudaStream_t st) {
     long long grid = (long long)per_sm * sms;
     if (grid > args.n_pairs) grid = args.n_pairs;
     if (grid > max_grid) grid = max_grid;
-    kern<<<(unsigned)grid, kThreads, smem, st>>>(args);
+    kern<<<(unsigned)grid, threads, smem, st>>>(args);
     return check_launch("screen_detect_radix");
 }
 
