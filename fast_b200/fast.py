@@ -664,6 +664,29 @@ class Fast():
             r = (r.real ** 2 + r.imag ** 2).contiguous()
         return dist.reduced_stats(r, db_lo, db_hi, nbins, already_global=True)
 
+    def compute_mean_irradiance(self, onaxis=True):
+        """Analytic (no Monte Carlo) mean coupled power from the residual PSD: long-exposure OTF
+        = exp(-D_phi) x pupil OTF (fast/fast.py:736-761).  Host numpy on the device-built PSD;
+        one-off N x N transforms, not on the hot path."""
+        def ift2(a, df):
+            ax = (-1, -2)
+            return numpy.fft.ifftshift(numpy.fft.ifft2(numpy.fft.ifftshift(a, axes=ax)), axes=ax) * (a.shape[-1] * df) ** 2
+
+        def ft2(a, dx):
+            ax = (-1, -2)
+            return numpy.fft.fftshift(numpy.fft.fft2(numpy.fft.fftshift(a, axes=ax)), axes=ax) * dx ** 2
+
+        W = self.powerspec
+        pupil = numpy.zeros(W.shape)
+        pupil[:self.pupil.shape[0], :self.pupil.shape[1]] = self.pupil * self.pupil_mode
+        cov = ift2(W, self.freq.df)
+        mid = (cov.shape[0] // 2, cov.shape[1] // 2)
+        structure = cov[mid] - cov
+        pupil_otf = ift2(numpy.abs(ft2(pupil, self.dx)) ** 2, self.freq.df) / (2 * numpy.pi) ** 2
+        otf = numpy.exp(-structure) * pupil_otf
+        psf = ft2(otf, self.dx).real if not onaxis else otf.sum().real * self.dx ** 2
+        return psf * self.diffraction_limit / (pupil.sum() * self.dx ** 2) ** 2
+
     # ------------------------------------------------------------------ FITS (optional dep)
     def make_header(self, params):
         from astropy.io import fits
