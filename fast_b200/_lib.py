@@ -83,6 +83,8 @@ _SIGS = {
     'fastb_screen_detect': (C.c_int, [C.POINTER(RunParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.POINTER(Subharm), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                       C.c_void_p]),
+    'fastb_screens_crop': (C.c_int, [C.POINTER(RunParams), C.c_void_p, C.c_void_p, C.POINTER(Subharm), C.c_void_p,
+                                     C.c_void_p, C.c_int64, C.c_void_p]),
     'fastb_rng_dump': (C.c_int, [C.c_uint64, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_int64,
                                  C.c_void_p, C.c_void_p]),
     'fastb_layer_screens_workspace_bytes': (C.c_int64, [C.c_int32, C.c_int32]),
@@ -203,6 +205,18 @@ def screen_detect(rp: RunParams, weight, U, out_a, out_b, workspace, chi=None, n
                                    _ptr(noise), sh, _ptr(out_a, f32), _ptr(out_b, f32), _ptr(workspace),
                                    workspace.numel() * workspace.element_size(), _stream()),
            'fastb_screen_detect')
+
+
+def screens_crop(rp: RunParams, weight, phs, workspace, noise=None, subharm=None):
+    """Materialise the cropped screens of the pairs described by rp into phs (2*n_pairs, P, P)."""
+    f32 = torch.float32
+    sh = None
+    if subharm is not None:
+        sh = C.byref(Subharm(_ptr(subharm['weight'], f32), _ptr(subharm.get('noise'), f32),
+                             _ptr(subharm['ex'], f32), _ptr(subharm['ey'], f32), _ptr(subharm['mean'], f32)))
+    _check(lib.fastb_screens_crop(C.byref(rp), _ptr(weight, f32), _ptr(noise), sh, _ptr(phs, f32),
+                                  _ptr(workspace), workspace.numel() * workspace.element_size(), _stream()),
+           'fastb_screens_crop')
 
 
 def rng_dump(seed, pair, n, device, chi_first=0, chi_count=0, want_tile=True):

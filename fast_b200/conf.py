@@ -35,7 +35,9 @@ DEFAULTS = {
 #          'numpy'  : noise drawn on the host from funcs._R in the reference's order
 #                     (bit-compatible stream; results match the reference to fp32 accuracy)
 #   DEVICE torch device string; default = current CUDA device
-EXTRA_DEFAULTS = {'RNG': 'device', 'DEVICE': None}
+#   KEEP_PHS  True: with RNG='numpy', also materialise each chunk's cropped screens in `sim.phs`
+#          (slow inspection path, fastb_screens_crop); default False -- screens never reach HBM
+EXTRA_DEFAULTS = {'RNG': 'device', 'DEVICE': None, 'KEEP_PHS': False}
 
 
 class ConfigParser():

@@ -38,6 +38,7 @@ struct RunArgs {
     const float2* sh_ex;      // 3*n_pup
     const float2* sh_ey;      // 3*n_pup
     const float2* sh_mean;    // 27
+    float* phs;               // direct kernel only: write the cropped screens instead of detecting
 };
 
 // ---- sub-harmonic term (include/fastb.h FastbSubharm) ------------------------------------
@@ -412,6 +413,20 @@ __global__ void __launch_bounds__(kThreads) screen_detect_direct(const __grid_co
                 ti += kk;
                 if (ti >= N) ti -= N;
             }
+            if (a.phs) {     // inspection seam (fastb_screens_crop): store phi, skip the detector
+                const float sgn = ((kk + c + lo) & 1) ? -1.f : 1.f;
+                float2 ph = make_float2(sgn * sr, sgn * si);
+                if (SH) {
+                    const float2 ex[3] = {a.sh_ex[c], a.sh_ex[P + c], a.sh_ex[2 * P + c]};
+                    const float2 sp = sh_phase(sh_tab + rr * kShTab, ex);
+                    ph.x += sp.x;
+                    ph.y += sp.y;
+                }
+                float* dst = a.phs + (size_t)pair * 2 * P * P + (size_t)rr * P + c;
+                dst[0] = ph.x;
+                dst[(size_t)P * P] = ph.y;
+                continue;
+            }
             const float uu = a.u_t[(size_t)c * P + rr];
             if (SH) {
                 const float sgn = ((kk + c + lo) & 1) ? -1.f : 1.f;
@@ -421,6 +436,10 @@ __global__ void __launch_bounds__(kThreads) screen_detect_direct(const __grid_co
             } else {
                 accumulate(make_float2(sr, si), uu, ((kk + c + lo) & 1) ? -uu : uu, acc);
             }
+        }
+        if (a.phs) {
+            __syncthreads();          // scratch and tables are reused by the next pair
+            continue;
         }
         finish_pair(a, pair, acc, red);
     }
@@ -600,6 +619,7 @@ extern "C" int fastb_screen_detect(const FastbRunParams* p, const float* d_weigh
     a.out_b = d_out_b;
     a.scratch = (float2*)((char*)d_workspace + ut);
     a.rows_per_block = direct_rows(p->n);
+    a.phs = nullptr;
     a.sh_weight = nullptr;
     a.sh_noise = a.sh_ex = a.sh_ey = a.sh_mean = nullptr;
     if (sh) {
@@ -656,4 +676,55 @@ extern "C" int fastb_rng_dump(uint64_t seed, int64_t pair, int32_t n, float* d_n
     rng_dump_kernel<<<(unsigned)((work + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         seed, (unsigned long long)pair, n, (float2*)d_noise_tile, chi_first, chi_count, d_chi_normals);
     return check_launch("rng_dump_kernel");
+}
+
+extern "C" int fastb_screens_crop(const FastbRunParams* p, const float* d_weight, const float* d_noise,
+                                  const FastbSubharm* sh, float* d_phs, void* d_workspace,
+                                  int64_t workspace_bytes, void* stream) {
+    int rc = validate_run(p);
+    if (rc) return rc;
+    FASTB_REQUIRE(d_weight && d_phs && d_workspace, "fastb_screens_crop: NULL pointer");
+    if (p->n_pairs == 0) return FASTB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t ut = align_up(sizeof(float) * (size_t)p->n_pup * p->n_pup, 256);
+    const size_t slot = (size_t)p->n * p->n_pup * sizeof(float2);
+    FASTB_REQUIRE(workspace_bytes >= (int64_t)(ut + slot), "fastb_screens_crop: workspace too small");
+    long long max_grid = (long long)(((size_t)workspace_bytes - ut) / slot);
+    RunArgs a = {};
+    a.n = p->n;
+    a.n_pup = p->n_pup;
+    a.lo = p->lo;
+    a.n_pairs = p->n_pairs;
+    a.first_pair = p->first_pair;
+    a.ppc = p->pairs_per_chunk;
+    a.seed = p->seed;
+    a.weight = d_weight;
+    a.noise = (const float2*)d_noise;
+    a.scratch = (float2*)((char*)d_workspace + ut);
+    a.rows_per_block = direct_rows(p->n);
+    a.phs = d_phs;
+    if (sh) {
+        FASTB_REQUIRE(sh->d_weight && sh->d_ex && sh->d_ey && sh->d_mean,
+                      "fastb_screens_crop: sub-harmonic tables must not be NULL");
+        FASTB_REQUIRE((sh->d_noise == nullptr) == (d_noise == nullptr),
+                      "fastb_screens_crop: d_noise and sh->d_noise must both be given or both be NULL");
+        a.sh_weight = sh->d_weight;
+        a.sh_noise = (const float2*)sh->d_noise;
+        a.sh_ex = (const float2*)sh->d_ex;
+        a.sh_ey = (const float2*)sh->d_ey;
+        a.sh_mean = (const float2*)sh->d_mean;
+    }
+    const bool rng = d_noise == nullptr, has_sh = sh != nullptr;
+    const size_t smem = direct_smem_bytes(p->n, has_sh, p->n_pup);
+    void (*kern)(RunArgs) = nullptr;
+    if (has_sh) kern = rng ? screen_detect_direct<true, true> : screen_detect_direct<false, true>;
+    else kern = rng ? screen_detect_direct<true, false> : screen_detect_direct<false, false>;
+    FASTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int sms = 0;
+    if ((rc = sm_count(&sms))) return rc;
+    long long grid = 2LL * sms;
+    if (grid > p->n_pairs) grid = p->n_pairs;
+    if (grid > max_grid) grid = max_grid;
+    kern<<<(unsigned)grid, kThreads, smem, st>>>(a);
+    return check_launch("screen_detect_direct(screens)");
 }

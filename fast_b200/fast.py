@@ -542,6 +542,23 @@ class Fast():
             out_b = torch.view_as_complex(out_b.view(-1, 2))
         return out_a, out_b
 
+    def screens(self, first_pair, n_pairs, noise=None, noise_lo=None):
+        """The cropped phase screens of global pairs [first_pair, first_pair + n_pairs) as a
+        (2 n_pairs, Npup, Npup) float32 device tensor ordered [Re_0, Im_0, Re_1, Im_1, ...]
+        (inspection seam, fastb_screens_crop; the run itself never materialises screens)."""
+        rp = self._run_params(n_pairs, first_pair, _lib.ALGO_DIRECT)
+        P = self.Npxls_pup
+        phs = torch.empty((2 * n_pairs, P, P), dtype=torch.float32, device=self.device)
+        if n_pairs:
+            nz = None if noise is None else torch.view_as_real(noise.contiguous())
+            sh = None
+            if self.subharmonics:
+                sh = dict(self._d['subharm'])
+                if noise_lo is not None:
+                    sh['noise'] = torch.view_as_real(noise_lo.contiguous())
+            _lib.screens_crop(rp, self._d['weight'], phs, self._workspace(rp), noise=nz, subharm=sh)
+        return phs
+
     def compute_logamp(self):
         """RNG='numpy': host draws in the reference's order (fast/fast.py:639-645);
         RNG='device': chi is generated inside the kernel and this only clears the buffer."""
@@ -575,7 +592,12 @@ class Fast():
             if self.subharmonics:       # drawn after the main block, like fast/fast.py:600
                 lo = funcs.generate_random_coefficients((J2, 3, 3, 3)).astype(numpy.complex64)
                 self._d['noise_lo'] = torch.from_numpy(lo.reshape(J2, 27)).to(self.device)
-        return None
+            if self.params.get('KEEP_PHS', False):
+                # opt-in: also materialise this chunk's screens in the reference's layout
+                # (J, Npup, Npup) = [Re screens | Im screens] (fast/funcs.py:220-221, fast/fast.py:596)
+                s = self.screens(chunk * J2, J2, noise=self._d['noise'], noise_lo=self._d.get('noise_lo'))
+                self.phs = torch.cat([s[0::2], s[1::2]]).cpu().numpy().astype(float)
+        return self.phs
 
     def compute_phs_temporal(self, chunk=0):
         """TEMPORAL mode (fast/fast.py:607-637).  Chunk 0: one real screen per layer on the

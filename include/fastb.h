@@ -204,6 +204,15 @@ int fastb_screen_detect(const FastbRunParams* p, const float* d_weight, const fl
                         float* d_out_a, float* d_out_b, void* d_workspace,
                         int64_t workspace_bytes, void* stream);
 
+/* Verification / inspection seam: the cropped phase screens themselves, as the reference keeps
+ * them in `Fast.phs` (fast/fast.py:596, shape (J, n_pup, n_pup)).  Same inputs and numbering as
+ * fastb_screen_detect; d_phs receives, for pair index p of this call, the Re screen at
+ * [2p] and the Im screen at [2p+1], each n_pup*n_pup floats, row-major.  Slow path (direct
+ * DFT), any even N <= 4096; the Monte-Carlo run never materialises screens. */
+int fastb_screens_crop(const FastbRunParams* p, const float* d_weight, const float* d_noise,
+                       const FastbSubharm* sh, float* d_phs, void* d_workspace,
+                       int64_t workspace_bytes, void* stream);
+
 /* Debug / verification aid: materialise the device-RNG noise tile of pair g (N*N complex64)
  * and the chi normals of realisations [first, first+count).  Either output may be NULL. */
 int fastb_rng_dump(uint64_t seed, int64_t pair, int32_t n, float* d_noise_tile,

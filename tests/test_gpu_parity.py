@@ -273,3 +273,27 @@ def test_elevation_sweep_matches_individual_runs(fast):
     means = [r.dB_rel.mean() for r in res]
     assert means[0] < means[1] < means[2]
     assert sims[0].L > sims[-1].L and sims[0].h[0] > sims[-1].h[0]
+
+
+# ---------------------------------------------------------------------------------------------
+# screen-level parity: the cropped screens themselves against the reference's `sim.phs`
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('name', ['mini_ao', 'mini_subharm', 'c1prime', 'c2', 'c4'])
+def test_screens_match_reference_phs(fast, name):
+    g, p = load_golden(name)
+    sim = fast.Fast(dict(p, RNG='numpy', KEEP_PHS=True))
+    sim.run()
+    J = sim.Niter_per_chunk
+    assert sim.phs.shape == (J, sim.Npxls_pup, sim.Npxls_pup)
+    if 'phs_last_all' in g:
+        assert rel(sim.phs, g['phs_last_all']) < 5e-6
+    else:
+        assert rel(sim.phs[0], g['phs_last_re0']) < 5e-6
+        assert rel(sim.phs[J // 2], g['phs_last_im0']) < 5e-6
+    # and with device RNG against the oracle fed the restated Philox noise
+    init = fo.build(p)
+    scr = sim.screens(5, 1).cpu().numpy()
+    want = fo.screens_from_noise(fo.device_noise_pair(sim._run_seed(), 5, init['N'])[None],
+                                 init['powerspec'], init['df'], init['lo'], init['hi'])
+    if name != 'mini_subharm':
+        assert rel(scr, want) < 2e-5
