@@ -131,6 +131,16 @@ def _cpu_worker_step(n_real):
     return done
 
 
+def cpu_psd_build_seconds(workload):
+    """Wall time of the oracle's whole init (PSD build dominated by the aliasing sum), 1 core."""
+    from oracle import configs, fast_oracle as fo
+    factory, _, _ = WORKLOADS[workload]
+    p = getattr(configs, factory)(niter=2, nchunks=1)
+    t0 = time.perf_counter()
+    fo.build(p)
+    return time.perf_counter() - t0
+
+
 def cpu_throughput(workload, n_proc, n_real_per_proc, steps=1, warmup=0):
     """realisations/s of the numpy oracle port on n_proc host processes."""
     import multiprocessing as mp
@@ -256,6 +266,15 @@ def run_ours(args):
         step(i)
     torch.cuda.synchronize()
 
+    # K1 (once-per-config PSD build): wall time of Fast.compute_powerspec -- pupil-filter DFT,
+    # fused PSD kernel, Simpson reductions and the small host<->device copies around them
+    k1_ms = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        sim.compute_powerspec()
+        torch.cuda.synchronize()
+        k1_ms.append(1e3 * (time.perf_counter() - t0))
+
     sampler = ClockSampler(local)
     sampler.start()
     if world > 1:
@@ -337,7 +356,8 @@ def run_ours(args):
         if world == 1 and not args.no_cpu:
             n_cpu = {'c2': 2000, 'c4': 500, 'c5': 120}[args.workload]
             v, dt = cpu_throughput(args.workload, 1, n_cpu)
-            cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+            k1_cpu = cpu_psd_build_seconds(args.workload)
+            cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "psd_build_s": k1_cpu,
                    "sample": f"{n_cpu} realizations of the same workload, 1 process, numpy oracle port "
                              f"of the reference chunk loop ({dt:.1f} s)"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -355,6 +375,8 @@ def run_ours(args):
                              "realizations_per_launch": n_real},
                 "cpu_baseline": cpu,
                 "comparator": comparator,
+                "k1_psd_build": {"compute_powerspec_ms": min(k1_ms), "note": "K1 + Simpson + pupil filter incl. host glue; "
+                                 "CPU counterpart is cpu_baseline.psd_build_s"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": int(launches),
                 "clocks": sampler.summary(),
