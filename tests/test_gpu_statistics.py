@@ -67,3 +67,57 @@ def test_screen_statistics_variance_law():
     half = r.size // 2
     assert abs(np.corrcoef(x[:half], x[half:])[0, 1]) < 0.03
     assert 0.3 < r.mean() < 0.75
+
+
+def _compare_db(db, db_ref, label):
+    """mean / variance within 1 % (+3 bootstrap SE of the reference sample), KS p > 0.01."""
+    rng = np.random.default_rng(0)
+    boot = rng.choice(db_ref, size=(200, db_ref.size), replace=True)
+    se_mean, se_var = boot.mean(1).std(), boot.var(1).std()
+    mean_tol = 0.01 * abs(db_ref.mean()) + 3 * se_mean
+    var_tol = 0.01 * db_ref.var() + 3 * se_var
+    ks = stats.ks_2samp(db, db_ref)
+    print(f'{label}: mean ref {db_ref.mean():.4f} gpu {db.mean():.4f} (tol {mean_tol:.4f}); var ref '
+          f'{db_ref.var():.4f} gpu {db.var():.4f} (tol {var_tol:.4f}); KS D={ks.statistic:.5f} p={ks.pvalue:.3f}')
+    assert abs(db.mean() - db_ref.mean()) < mean_tol
+    assert abs(db.var() - db_ref.var()) < var_tol
+    assert ks.pvalue > 0.01
+
+
+def _golden_dist(fname):
+    path = os.path.join(GOLDEN, fname)
+    if not os.path.exists(path):
+        pytest.skip(f'{fname} not generated')
+    return np.load(path)['r']
+
+
+def test_c3_low_elevation_distribution_matches_reference():
+    """C3 sample at 10 degrees elevation: strong turbulence, deep fades (mean about -14 dB)."""
+    import fast_b200
+    ref = _golden_dist('c3_el10_dist_5e4.npz').astype(float)
+    _, p = load_golden('c3_el10')
+    sim = fast_b200.Fast(dict(p, NITER=500000, NCHUNKS=10, SEED=7))
+    _compare_db(sim.run().dB_rel, 10 * np.log10(ref), 'c3_el10')
+
+
+def test_c4_coherent_distribution_matches_reference():
+    """C4 (512 x 512, coherent): modulus in dB and the phase of the complex field."""
+    import fast_b200
+    ref = _golden_dist('c4_dist_5e4.npz').astype(complex)
+    _, p = load_golden('c4')
+    sim = fast_b200.Fast(dict(p, NITER=200000, NCHUNKS=10, SEED=8))
+    z = sim.run()._r
+    assert z.dtype == complex
+    _compare_db(20 * np.log10(np.abs(z)), 20 * np.log10(np.abs(ref)), 'c4 |z|^2')
+    ks = stats.ks_2samp(np.angle(z), np.angle(ref))
+    print(f'c4 phase: std ref {np.angle(ref).std():.4f} gpu {np.angle(z).std():.4f}; KS p={ks.pvalue:.3f}')
+    assert ks.pvalue > 0.01
+
+
+def test_c5_large_grid_distribution_matches_reference():
+    """C5 (1024 x 1024): 1e5 device-RNG realisations vs 1e4 reference realisations."""
+    import fast_b200
+    ref = _golden_dist('c5_dist_1e4.npz').astype(float)
+    _, p = load_golden('c5')
+    sim = fast_b200.Fast(dict(p, NITER=100000, NCHUNKS=10, SEED=9))
+    _compare_db(sim.run().dB_rel, 10 * np.log10(ref), 'c5')
