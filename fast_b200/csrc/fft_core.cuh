@@ -102,7 +102,9 @@ struct LineFFT {
     static constexpr int S2 = kThree ? S1 / 16 : 1;
     static constexpr int SF = kThree ? S2 : S1;             // length of the last small DFTs
     static constexpr bool kHasC = (SF > 1);
-    static constexpr int kPadA = kThree ? S2 : 0;
+    // exchange-A padding: S2 == 1 uses 2 so that each thread's 16 gathered values are 16-byte
+    // aligned (128-bit shared loads, conflict-free at a 144-byte lane stride)
+    static constexpr int kPadA = kThree ? (S2 == 1 ? 2 : S2) : 0;
     static constexpr int kBufA = 16 * (S1 + kPadA);         // exchange A layout: a*(S1+pad)+t
     static constexpr int kBufC = 17 * S1;                   // exchange C layout: u*17 + e
     static constexpr int kBuf = (kBufA > kBufC) ? kBufA : kBufC;   // float2 per line
@@ -111,19 +113,37 @@ struct LineFFT {
     // element index held in register m of thread t before phase A
     FASTB_HD static int n_in(int t, int m) { return t + S1 * m; }
 
-    // Twiddle tables (thread-major inner index => conflict-free shared-memory reads):
-    //   twa[a * S1 + t]  = exp(+2 pi i (t a) / N)          a < 16, t < S1      (N entries)
-    //   twb[a2 * S2 + t2] = exp(+2 pi i (16 t2 a2) / N)    a2 < 16, t2 < S2    (S2 > 1 only)
-    static constexpr int kTwA = N;
-    static constexpr int kTwB = (kThree && S2 > 1) ? 16 * S2 : 0;
-    FASTB_HD static int twa_exponent(int idx) { return ((idx % S1) * (idx / S1)) & (N - 1); }
-    FASTB_HD static int twb_exponent(int idx) { return (16 * (idx % S2) * (idx / S2)) & (N - 1); }
+    // Twiddle tables, one row of kTwRow = 18 float2 per thread (16 used): the 144-byte row
+    // stride makes 128-bit shared loads of consecutive threads conflict-free.
+    //   twa[t * 18 + a]   = exp(+2 pi i (t a) / N)          t < S1, a < 16
+    //   twb[t2 * 18 + a2] = exp(+2 pi i (16 t2 a2) / N)     t2 < S2, a2 < 16   (S2 > 1 only)
+    static constexpr int kTwRow = 18;
+    static constexpr int kTwA = kTwRow * S1;
+    static constexpr int kTwB = (kThree && S2 > 1) ? kTwRow * S2 : 0;
+    FASTB_HD static int twa_exponent(int idx) {
+        const int t = idx / kTwRow, a = idx % kTwRow;
+        return a < 16 ? (t * a) & (N - 1) : 0;
+    }
+    FASTB_HD static int twb_exponent(int idx) {
+        const int t2 = idx / kTwRow, a2 = idx % kTwRow;
+        return a2 < 16 ? (16 * t2 * a2) & (N - 1) : 0;
+    }
+
+    // multiply v[1..15] by the 16 twiddles of one table row, fetched as 8 x 128-bit loads
+    FASTB_HD static void apply_twiddle_row(float2 (&v)[16], const float2* row) {
+        const float4* q = reinterpret_cast<const float4*>(row);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 w = q[j];
+            if (j > 0) v[2 * j] = cmul(v[2 * j], make_float2(w.x, w.y));
+            v[2 * j + 1] = cmul(v[2 * j + 1], make_float2(w.z, w.w));
+        }
+    }
 
     // phase A: dft16 over m, twiddle, write exchange buffer
     FASTB_HD static void phase_a(int t, float2 (&v)[16], const float2* twa, float2* buf) {
         dft16(v);
-#pragma unroll
-        for (int a = 1; a < 16; ++a) v[a] = cmul(v[a], twa[a * S1 + t]);
+        apply_twiddle_row(v, twa + t * kTwRow);
         if (kThree) {
 #pragma unroll
             for (int a = 0; a < 16; ++a) buf[a * (S1 + kPadA) + t] = v[a];
@@ -137,13 +157,21 @@ struct LineFFT {
     // and then call phase_b_store before phase C.
     FASTB_HD static void phase_b(int u, float2 (&v)[16], const float2* twb, const float2* buf) {
         const int a = u / S2, t2 = u % S2;
+        if (S2 == 1) {
+            // 16 contiguous, 16-byte aligned values: 8 x 128-bit loads
+            const float4* q = reinterpret_cast<const float4*>(buf + a * (S1 + kPadA));
 #pragma unroll
-        for (int m2 = 0; m2 < 16; ++m2) v[m2] = buf[a * (S1 + kPadA) + t2 + S2 * m2];
-        dft16(v);
-        if (S2 > 1) {
+            for (int j = 0; j < 8; ++j) {
+                const float4 w = q[j];
+                v[2 * j] = make_float2(w.x, w.y);
+                v[2 * j + 1] = make_float2(w.z, w.w);
+            }
+        } else {
 #pragma unroll
-            for (int a2 = 1; a2 < 16; ++a2) v[a2] = cmul(v[a2], twb[a2 * S2 + t2]);
+            for (int m2 = 0; m2 < 16; ++m2) v[m2] = buf[a * (S1 + kPadA) + t2 + S2 * m2];
         }
+        dft16(v);
+        if (S2 > 1) apply_twiddle_row(v, twb + t2 * kTwRow);
     }
 
     FASTB_HD static void phase_b_store(int u, const float2 (&v)[16], float2* buf) {
