@@ -183,6 +183,35 @@ __device__ void finish_pair(const RunArgs& a, long long pair, float (&acc)[4], f
 // Synchronise the S1 threads that share one line.  S1 <= 32: the line lives inside a warp.
 // S1 = 64 / 128 (N = 1024 / 2048): a named barrier per line (ids 1..LPB; 0 is __syncthreads),
 // so lines do not wait for each other.
+// ---- TMA bulk copy (cp.async.bulk, 1-D) + mbarrier helpers -----------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// global -> this CTA's shared memory; completion (byte count) is signalled on `bar`
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
 template <int S1>
 __device__ __forceinline__ void line_sync(int ln) {
     if (S1 > 32) asm volatile("bar.sync %0, %1;" ::"r"(ln + 1), "n"(S1) : "memory");
@@ -224,7 +253,8 @@ constexpr int radix_threads() { return LOG2N <= 8 ? 128 : 256; }
 template <int LOG2N>
 constexpr int radix_min_blocks() { return LOG2N <= 8 ? 4 : (LOG2N == 9 ? 2 : 3); }
 
-template <int LOG2N, bool RNG, bool SH, int THREADS = radix_threads<LOG2N>(), int MINB = radix_min_blocks<LOG2N>()>
+template <int LOG2N, bool RNG, bool SH, int THREADS = radix_threads<LOG2N>(), int MINB = radix_min_blocks<LOG2N>(),
+          int TMA = 0>
 __global__ void __launch_bounds__(THREADS, MINB)
 screen_detect_radix(const __grid_constant__ RunArgs a) {
     using F = LineFFT<LOG2N>;
@@ -234,14 +264,29 @@ screen_detect_radix(const __grid_constant__ RunArgs a) {
     float2* twa = reinterpret_cast<float2*>(smem_raw);
     float2* twb = twa + F::kTwA;
     float2* bufs = twb + F::kTwB;
-    float* red = reinterpret_cast<float*>(bufs + LPB * F::kBuf);
-    float2* sh_amp = reinterpret_cast<float2*>(red + 4 * (THREADS / 32));     // SH only
+    // TMA staging (lines that fit in a warp): each warp's input of one iteration -- its weight
+    // rows in pass 1, its scratch columns in pass 2 -- is one contiguous block of global memory,
+    // fetched by a single cp.async.bulk one iteration ahead into a 4 KB per-warp stage
+    constexpr bool kTma = (S1 <= 32) && TMA != 0;
+    constexpr bool kTmaW = kTma && (TMA == 1 || TMA == 3);      // weight rows through the stage
+    constexpr bool kTmaT = kTma && (TMA == 1 || TMA == 2);      // scratch columns through the stage
+    constexpr int kLinesPerWarp = kTma ? 32 / S1 : 1;
+    constexpr int kWarps = THREADS / 32;
+    unsigned char* stage_all = reinterpret_cast<unsigned char*>(bufs + LPB * F::kBuf);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stage_all + (kTma ? kWarps * 4096 : 0));
+    float* red = reinterpret_cast<float*>(bars + (kTma ? kWarps : 0));
+    float2* sh_amp = reinterpret_cast<float2*>(red + 4 * kWarps);     // SH only
     float2* sh_tab = sh_amp + 28;
 
     const int tid = threadIdx.x;
     const int ln = tid / S1, u = tid % S1;
+    const int warp = tid >> 5, lane = tid & 31;
     float2* buf = bufs + ln * F::kBuf;
     const int P = a.n_pup, lo = a.lo;
+    unsigned char* stage = stage_all + warp * 4096;
+    uint64_t* bar = bars + warp;
+    uint32_t parity = 0;
+    if (kTma && lane == 0) mbar_init(bar, 1);
 
     for (int j = tid; j < F::kTwA + F::kTwB; j += THREADS) {
         const int ex = j < F::kTwA ? F::twa_exponent(j) : F::twb_exponent(j - F::kTwA);
@@ -264,22 +309,77 @@ screen_detect_radix(const __grid_constant__ RunArgs a) {
     for (int e = 0; e < 16; ++e)
         if ((unsigned)(kb + F::k_off(e)) < (unsigned)P) need |= 1u << e;
 
+    // Enqueue this warp's input block of iteration `itn` (all lanes call it after a __syncwarp;
+    // lane 0 issues).  Nothing is issued -- and nothing will be waited for -- when the warp has
+    // no line inside the crop in that iteration.
+    auto prefetch = [&](int itn) {
+        const bool rows_n = itn < n1;
+        const int line0 = (rows_n ? itn : itn - n1) * LPB + warp * kLinesPerWarp;
+        if ((rows_n && !kTmaW) || (!rows_n && !kTmaT)) return;
+        const int nlines = rows_n ? kLinesPerWarp : min(kLinesPerWarp, P - line0);
+        if (nlines <= 0 || lane != 0) return;
+        const uint32_t bytes = (uint32_t)nlines * N * (rows_n ? 4u : 8u);
+        const void* src = rows_n ? (const void*)(a.weight + (size_t)line0 * N) : (const void*)(T + (size_t)line0 * N);
+        fence_proxy_async();                  // earlier generic reads of the stage precede the async write
+        mbar_expect_tx(bar, bytes);
+        bulk_g2s(stage, src, bytes, bar);
+    };
+    if (kTma) {
+        fence_proxy_async();                  // mbarrier init visible to the async proxy
+        __syncthreads();
+    }
+
     for (long long pair = blockIdx.x; pair < a.n_pairs; pair += gridDim.x) {
         const unsigned long long g = (unsigned long long)(a.first_pair + pair);
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
         if (SH) sh_prepare(a, pair, sh_amp, sh_tab);   // table visible after the barrier at it == n1
+        if (kTma) prefetch(0);
         for (int it = 0; it < n1 + n2; ++it) {
             const bool rows = it < n1;
-            if (it == n1) __syncthreads();            // every row of T is stored before a column is read
+            if (it == n1) {
+                if (kTma) fence_proxy_async();        // T was written through the generic proxy
+                __syncthreads();                      // every row of T is stored before a column is read
+                if (kTma) prefetch(n1);
+            }
             const int line = (rows ? it : it - n1) * LPB + ln;      // r' (pass 1) or c (pass 2)
             if (!rows) {
                 // last column iteration: warps whose lines all lie beyond the crop have nothing
                 // to do (line barriers involve only the threads of that line)
-                constexpr int kLinesPerWarp = S1 <= 32 ? 32 / S1 : 1;
                 if (line - (ln % kLinesPerWarp) >= P) continue;
             }
             float2 v[16];
-            if (rows) {
+            if ((rows && kTmaW) || (!rows && kTmaT)) {
+                mbar_wait(bar, parity);
+                parity ^= 1;
+                const int lw = ln % kLinesPerWarp;
+                if (rows) {
+                    const float* ws = reinterpret_cast<const float*>(stage) + lw * N;
+                    float w16[16];
+#pragma unroll
+                    for (int m = 0; m < 16; ++m) w16[m] = ws[u + S1 * m];
+                    __syncwarp();
+                    if (it + 1 < n1) prefetch(it + 1);
+                    if (RNG) {
+                        uint32_t mr[16], ma[16];
+                        noise_block_fields((uint32_t)(line * S1 + u), g, k0, k1, mr, ma);
+#pragma unroll
+                        for (int m = 0; m < 16; ++m) v[m] = weighted_normal_m(mr[m], ma[m], w16[m]);
+                    } else {
+                        const float2* nrow = a.noise + ((size_t)pair * N + line) * N;
+#pragma unroll
+                        for (int m = 0; m < 16; ++m) {
+                            const float2 nz = __ldg(nrow + u + S1 * m);
+                            v[m] = make_float2(nz.x * w16[m], nz.y * w16[m]);
+                        }
+                    }
+                } else {
+                    const float2* ts = reinterpret_cast<const float2*>(stage) + lw * N;
+#pragma unroll
+                    for (int m = 0; m < 16; ++m) v[m] = ts[u + S1 * m];
+                    __syncwarp();
+                    if (it + 1 < n1 + n2) prefetch(it + 1);
+                }
+            } else if (rows) {
                 const float* wrow = a.weight + (size_t)line * N;
                 if (RNG) {
                     uint32_t mr[16], ma[16];
@@ -474,10 +574,11 @@ size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 size_t sh_smem_bytes(bool sh, int n_pup) { return sh ? sizeof(float2) * (28 + (size_t)kShTab * n_pup) : 0; }
 
 template <int LOG2N>
-size_t radix_smem_bytes(bool sh, int n_pup, int threads = kThreads) {
+size_t radix_smem_bytes(bool sh, int n_pup, int threads = kThreads, bool use_tma = false) {
     using F = LineFFT<LOG2N>;
     const int LPB = threads / F::S1;
-    return sizeof(float2) * ((size_t)F::kTwA + F::kTwB + (size_t)LPB * F::kBuf) +
+    const size_t tma = (F::S1 <= 32 && use_tma) ? (size_t)(threads / 32) * (4096 + sizeof(uint64_t)) : 0;
+    return sizeof(float2) * ((size_t)F::kTwA + F::kTwB + (size_t)LPB * F::kBuf) + tma +
            sizeof(float) * 4 * (threads / 32) + sh_smem_bytes(sh, n_pup);
 }
 
@@ -508,26 +609,20 @@ int launch_radix(const RunArgs& args, bool rng, int max_grid, cudaStream_t st) {
     void (*kern)(RunArgs) = nullptr;
     if (sh) kern = rng ? screen_detect_radix<LOG2N, true, true> : screen_detect_radix<LOG2N, false, true>;
     else kern = rng ? screen_detect_radix<LOG2N, true, false> : screen_detect_radix<LOG2N, false, false>;
+    bool use_tma = false;
 #ifdef FASTB_TUNE
-    // tuning builds only: FASTB_VARIANT selects CTA size / CTAs per SM for the bench path
+    // tuning builds only: FASTB_TMA=1|2|3 routes weights+scratch / scratch only / weights only
+    // through per-warp TMA staging (cp.async.bulk + mbarrier) on the bench path
     if (rng && !sh) {
-        const char* e = getenv("FASTB_VARIANT");
+        const char* e = getenv("FASTB_TMA");
         const int v = e ? atoi(e) : 0;
-        if constexpr (LOG2N <= 9) {
-            if (v == 648) { kern = screen_detect_radix<LOG2N, true, false, 64, 8>; threads = 64; }
-            if (v == 6412) { kern = screen_detect_radix<LOG2N, true, false, 64, 12>; threads = 64; }
-            if (v == 5121) { kern = screen_detect_radix<LOG2N, true, false, 512, 1>; threads = 512; }
-        }
-        if constexpr (LOG2N <= 10) {
-            if (v == 1284) { kern = screen_detect_radix<LOG2N, true, false, 128, 4>; threads = 128; }
-            if (v == 1285) { kern = screen_detect_radix<LOG2N, true, false, 128, 5>; threads = 128; }
-            if (v == 1286) { kern = screen_detect_radix<LOG2N, true, false, 128, 6>; threads = 128; }
-        }
-        if (v == 2562) kern = screen_detect_radix<LOG2N, true, false, 256, 2>;
-        if (v == 2563) kern = screen_detect_radix<LOG2N, true, false, 256, 3>;
+        constexpr int T = radix_threads<LOG2N>(), M = radix_min_blocks<LOG2N>();
+        if (v == 1) { kern = screen_detect_radix<LOG2N, true, false, T, M, 1>; use_tma = true; }
+        if (v == 2) { kern = screen_detect_radix<LOG2N, true, false, T, M, 2>; use_tma = true; }
+        if (v == 3) { kern = screen_detect_radix<LOG2N, true, false, T, M, 3>; use_tma = true; }
     }
 #endif
-    const size_t smem = radix_smem_bytes<LOG2N>(sh, args.n_pup, threads);
+    const size_t smem = radix_smem_bytes<LOG2N>(sh, args.n_pup, threads, use_tma);
     FASTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     FASTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                                     cudaSharedmemCarveoutMaxShared));
@@ -591,6 +686,8 @@ extern "C" int fastb_screen_detect(const FastbRunParams* p, const float* d_weigh
     int rc = validate_run(p);
     if (rc) return rc;
     FASTB_REQUIRE(d_weight && d_U && d_out_a && d_out_b && d_workspace, "fastb_screen_detect: NULL pointer");
+    FASTB_REQUIRE(((uintptr_t)d_weight & 15) == 0 && ((uintptr_t)d_workspace & 255) == 0,
+                  "fastb_screen_detect: d_weight must be 16-byte and d_workspace 256-byte aligned");
     if (p->n_pairs == 0) return FASTB_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t ut = align_up(sizeof(float) * (size_t)p->n_pup * p->n_pup, 256);
