@@ -94,9 +94,123 @@ FASTB_HD void dft16(float2 (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = o[i];
 }
 
+// inverse 32-point DFT, natural order in and out: two 16-point DFTs of the even / odd samples
+// combined by one radix-2 stage, X[k] = E[k] + w32^k O[k], X[k+16] = E[k] - w32^k O[k]
+FASTB_HD void dft32(float2 (&v)[32]) {
+    constexpr float c[16] = {1.f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f,
+                             0.70710678118654752f, 0.55557023301960218f, 0.38268343236508977f,
+                             0.19509032201612825f, 0.f, -0.19509032201612825f, -0.38268343236508977f,
+                             -0.55557023301960218f, -0.70710678118654752f, -0.83146961230254524f,
+                             -0.92387953251128674f, -0.98078528040323043f};
+    constexpr float sn[16] = {0.f, 0.19509032201612825f, 0.38268343236508977f, 0.55557023301960218f,
+                              0.70710678118654752f, 0.83146961230254524f, 0.92387953251128674f,
+                              0.98078528040323043f, 1.f, 0.98078528040323043f, 0.92387953251128674f,
+                              0.83146961230254524f, 0.70710678118654752f, 0.55557023301960218f,
+                              0.38268343236508977f, 0.19509032201612825f};
+    float2 ev[16], od[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        ev[j] = v[2 * j];
+        od[j] = v[2 * j + 1];
+    }
+    dft16(ev);
+    dft16(od);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const float2 t = (k == 0) ? od[0] : (k == 8) ? cmuli(od[8]) : cmul(od[k], make_float2(c[k], sn[k]));
+        v[k] = cadd(ev[k], t);
+        v[k + 16] = csub(ev[k], t);
+    }
+}
+
+// Line FFT with 32 complex elements per thread for N = 512 (32 x 16) and N = 1024 (32 x 32):
+// S1 = N/32 threads per line, ONE shared-memory exchange per line.
+//   phase A  thread t holds x[t + S1 m], m < 32: 32-point DFT over m -> a = k mod 32, twiddle
+//            w_N^(t a), store buf[a][t]
+//   phase B  N = 1024: thread u = a gathers t < 32 and does a 32-point DFT -> b, k = a + 32 b
+//            N = 512 : thread u handles a = u and a = u + 16, a 16-point DFT each, k = a + 32 b
+template <int LOG2N>
+struct LineFFT32 {
+    static constexpr int N = 1 << LOG2N;
+    static constexpr int E = 32;                            // elements per thread
+    static constexpr int S1 = N / 32;                       // threads per line (16 or 32)
+    static_assert(LOG2N == 9 || LOG2N == 10, "LineFFT32 serves N = 512 and 1024");
+    static constexpr int kRowA = S1 + 2;                    // buf[a * kRowA + t]: 16-byte aligned rows,
+    static constexpr int kBuf = 32 * kRowA;                 // conflict-free 128-bit gathers
+    static constexpr int kTwRow = 34;                       // twa[t * 34 + a], a < 32
+    static constexpr int kTwA = kTwRow * S1;
+    static constexpr int kTwB = 0;
+    FASTB_HD static int n_in(int t, int m) { return t + S1 * m; }
+    FASTB_HD static int twa_exponent(int idx) {
+        const int t = idx / kTwRow, a = idx % kTwRow;
+        return a < 32 ? (t * a) & (N - 1) : 0;
+    }
+    FASTB_HD static int twb_exponent(int) { return 0; }
+
+    FASTB_HD static void phase_a(int t, float2 (&v)[32], const float2* twa, float2* buf) {
+        dft32(v);
+        const float4* q = reinterpret_cast<const float4*>(twa + t * kTwRow);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const float4 w = q[j];
+            if (j > 0) v[2 * j] = cmul(v[2 * j], make_float2(w.x, w.y));
+            v[2 * j + 1] = cmul(v[2 * j + 1], make_float2(w.z, w.w));
+        }
+#pragma unroll
+        for (int a = 0; a < 32; ++a) buf[a * kRowA + t] = v[a];
+    }
+
+    FASTB_HD static void phase_b(int u, float2 (&v)[32], const float2* buf) {
+        if (S1 == 32) {
+            const float4* q = reinterpret_cast<const float4*>(buf + u * kRowA);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float4 w = q[j];
+                v[2 * j] = make_float2(w.x, w.y);
+                v[2 * j + 1] = make_float2(w.z, w.w);
+            }
+            dft32(v);
+        } else {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float2 x[16];
+                const float4* q = reinterpret_cast<const float4*>(buf + (u + 16 * h) * kRowA);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 w = q[j];
+                    x[2 * j] = make_float2(w.x, w.y);
+                    x[2 * j + 1] = make_float2(w.z, w.w);
+                }
+                dft16(x);
+#pragma unroll
+                for (int b = 0; b < 16; ++b) v[16 * h + b] = x[b];
+            }
+        }
+    }
+
+    // the whole line FFT; `sync` synchronises the S1 threads of the line
+    template <typename Sync>
+    FASTB_HD static void run(int u, float2 (&v)[32], const float2* twa, const float2*, float2* buf, Sync sync) {
+        phase_a(u, v, twa, buf);
+        sync();
+        phase_b(u, v, buf);
+        sync();                 // buffer may be rewritten by the next line
+    }
+
+    FASTB_HD static int k_base(int u) { return u; }
+    FASTB_HD static constexpr int k_off(int e) { return S1 == 32 ? 32 * e : 16 * (e / 16) + 32 * (e % 16); }
+    FASTB_HD static int k_out(int u, int e) { return k_base(u) + k_off(e); }
+    FASTB_HD static constexpr bool k_off_all_even() {
+        for (int e = 0; e < 32; ++e)
+            if (k_off(e) & 1) return false;
+        return true;
+    }
+};
+
 template <int LOG2N>
 struct LineFFT {
     static constexpr int N = 1 << LOG2N;
+    static constexpr int E = 16;                            // elements per thread
     static constexpr int S1 = N / 16;                       // threads per line
     static constexpr bool kThree = (S1 >= 16);              // N >= 256
     static constexpr int S2 = kThree ? S1 / 16 : 1;
@@ -203,6 +317,25 @@ struct LineFFT {
                 for (int q = 0; q < 8; ++q) v[i * SF + q] = w[q];
             }
         }
+    }
+
+    // the whole line FFT; `sync` synchronises the S1 threads of the line
+    template <typename Sync>
+    FASTB_HD static void run(int u, float2 (&v)[16], const float2* twa, const float2* twb, float2* buf, Sync sync) {
+        phase_a(u, v, twa, buf);
+        sync();
+        if (kThree) {
+            phase_b(u, v, twb, buf);
+            if (S2 > 1) {
+                sync();
+                phase_b_store(u, v, buf);
+                sync();
+                phase_c(u, v, buf);
+            }
+        } else {
+            phase_c(u, v, buf);
+        }
+        sync();                 // buffer may be rewritten by the next line
     }
 
     // Output index k held in register e of thread u after the last phase, split into a

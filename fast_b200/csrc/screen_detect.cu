@@ -180,9 +180,6 @@ __device__ void finish_pair(const RunArgs& a, long long pair, float (&acc)[4], f
     __syncthreads();
 }
 
-// Synchronise the S1 threads that share one line.  S1 <= 32: the line lives inside a warp.
-// S1 = 64 / 128 (N = 1024 / 2048): a named barrier per line (ids 1..LPB; 0 is __syncthreads),
-// so lines do not wait for each other.
 // ---- TMA bulk copy (cp.async.bulk, 1-D) + mbarrier helpers -----------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -212,68 +209,67 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
+// Synchronise the S1 threads that share one line.  S1 <= 32: the line lives inside a warp.
+// S1 = 64 / 128: a named barrier per line (ids 1..LPB; 0 is __syncthreads), so lines do not
+// wait for each other.
 template <int S1>
-__device__ __forceinline__ void line_sync(int ln) {
-    if (S1 > 32) asm volatile("bar.sync %0, %1;" ::"r"(ln + 1), "n"(S1) : "memory");
-    else __syncwarp();
-}
-
-// run phases A..C of the line FFT on v (see fft_core.cuh); u = thread index within the line
-template <int LOG2N>
-__device__ __forceinline__ void line_fft(int ln, int u, float2 (&v)[16], const float2* twa, const float2* twb,
-                                         float2* buf) {
-    using F = LineFFT<LOG2N>;
-    F::phase_a(u, v, twa, buf);
-    line_sync<F::S1>(ln);
-    if (F::kThree) {
-        F::phase_b(u, v, twb, buf);
-        if (F::S2 > 1) {
-            line_sync<F::S1>(ln);
-            F::phase_b_store(u, v, buf);
-            line_sync<F::S1>(ln);
-            F::phase_c(u, v, buf);
-        }
-    } else {
-        F::phase_c(u, v, buf);
+struct LineSync {
+    int ln;
+    __device__ __forceinline__ void operator()() const {
+        if (S1 > 32) asm volatile("bar.sync %0, %1;" ::"r"(ln + 1), "n"(S1) : "memory");
+        else __syncwarp();
     }
-    line_sync<F::S1>(ln);        // buffer may be rewritten by the next line
-}
+};
+
+// Line-FFT flavour and CTA shape per grid size, measured on B200 (profiles/)
+//   N <= 256 : 128 threads x 4 CTAs/SM (128 registers) -- small CTAs keep the three per-pair
+//              barriers cheap and balance the pupil columns over 8 lines per iteration
+//   N  = 512 : 256 threads x 2 CTAs/SM (125 registers); N >= 1024: 256 x 3 (80 registers)
+// All use the 16-elements-per-thread FFT.  A 32-elements-per-thread flavour (512 = 32 x 16,
+// 1024 = 32 x 32: one exchange per line, 168 registers) is kept for tuning builds
+// (FASTB_TUNE, FASTB_E=32): it measured the same throughput in every CTA shape -- the kernel is
+// bound by register-file-limited ILP x TLP, not by the number of shared-memory exchanges.
+template <int LOG2N, int E>
+struct RadixCfg;
+template <int LOG2N>
+struct RadixCfg<LOG2N, 16> {
+    using F = LineFFT<LOG2N>;
+    static constexpr int kThreadsPerCta = LOG2N <= 8 ? 128 : 256;
+    static constexpr int kMinBlocks = LOG2N <= 8 ? 4 : (LOG2N == 9 ? 2 : 3);
+};
+template <int LOG2N>
+struct RadixCfg<LOG2N, 32> {
+    using F = LineFFT32<LOG2N>;
+    static constexpr int kThreadsPerCta = 128;
+    static constexpr int kMinBlocks = 3;
+};
+template <int LOG2N>
+constexpr int radix_default_e() { return 16; }
 
 // One loop body serves both passes (keeps the kernel inside the instruction cache): iterations
 // [0, n1) are frequency rows (noise -> FFT -> pruned store to T[c][r']), iterations [n1, n1+n2)
-// are kept columns (load T[c][:] -> FFT -> detector accumulation).  No CTA-wide barrier inside a
-// pass when a line fits in a warp (N <= 512).
-// CTA shape per grid size, measured on B200 (profiles/):
-//   N <= 256 : 128 threads x 4 CTAs/SM (128 registers) -- small CTAs keep the three per-pair
-//              barriers cheap and balance the 82 pupil columns over 8 lines per iteration
-//   N  = 512 : 256 threads x 2 CTAs/SM (128 registers) -- more CTAs thrash L2 with scratch
-//   N >= 1024: 256 threads x 3 CTAs/SM (80 registers)
-template <int LOG2N>
-constexpr int radix_threads() { return LOG2N <= 8 ? 128 : 256; }
-template <int LOG2N>
-constexpr int radix_min_blocks() { return LOG2N <= 8 ? 4 : (LOG2N == 9 ? 2 : 3); }
-
-template <int LOG2N, bool RNG, bool SH, int THREADS = radix_threads<LOG2N>(), int MINB = radix_min_blocks<LOG2N>(),
-          int TMA = 0>
-__global__ void __launch_bounds__(THREADS, MINB)
-screen_detect_radix(const __grid_constant__ RunArgs a) {
-    using F = LineFFT<LOG2N>;
-    constexpr int N = F::N, S1 = F::S1, LPB = THREADS / S1;
+// are kept columns (load T[c][:] -> FFT -> detector accumulation).  No CTA-wide barrier inside
+// a pass.  TMA != 0 (tuning builds, E = 16, lines inside a warp): the warp's contiguous input
+// block of the next iteration is fetched by one cp.async.bulk into a per-warp stage
+// (1: weights and scratch, 2: scratch only, 3: weights only) -- measured slower, off by default.
+template <class F, bool RNG, bool SH, int THREADS, int MINB, int TMA = 0>
+__global__ void __launch_bounds__(THREADS, MINB) screen_detect_radix(const __grid_constant__ RunArgs a) {
+    constexpr int N = F::N, S1 = F::S1, E = F::E, LPB = THREADS / S1;
     static_assert(THREADS % S1 == 0 && LPB >= 1 && (S1 <= 32 || LPB <= 15), "line/barrier layout");
+    static_assert(E == 16 || E == 32, "elements per thread");
+    constexpr bool kTma = (S1 <= 32) && TMA != 0 && E == 16;
+    constexpr bool kTmaW = kTma && (TMA == 1 || TMA == 3);      // weight rows through the stage
+    constexpr bool kTmaT = kTma && (TMA == 1 || TMA == 2);      // scratch columns through the stage
+    constexpr int kLinesPerWarp = S1 <= 32 ? 32 / S1 : 1;
+    constexpr int kWarps = THREADS / 32;
+    constexpr int kStageBytes = 32 * E * 8;
+
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* twa = reinterpret_cast<float2*>(smem_raw);
     float2* twb = twa + F::kTwA;
     float2* bufs = twb + F::kTwB;
-    // TMA staging (lines that fit in a warp): each warp's input of one iteration -- its weight
-    // rows in pass 1, its scratch columns in pass 2 -- is one contiguous block of global memory,
-    // fetched by a single cp.async.bulk one iteration ahead into a 4 KB per-warp stage
-    constexpr bool kTma = (S1 <= 32) && TMA != 0;
-    constexpr bool kTmaW = kTma && (TMA == 1 || TMA == 3);      // weight rows through the stage
-    constexpr bool kTmaT = kTma && (TMA == 1 || TMA == 2);      // scratch columns through the stage
-    constexpr int kLinesPerWarp = kTma ? 32 / S1 : 1;
-    constexpr int kWarps = THREADS / 32;
     unsigned char* stage_all = reinterpret_cast<unsigned char*>(bufs + LPB * F::kBuf);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(stage_all + (kTma ? kWarps * 4096 : 0));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stage_all + (kTma ? kWarps * kStageBytes : 0));
     float* red = reinterpret_cast<float*>(bars + (kTma ? kWarps : 0));
     float2* sh_amp = reinterpret_cast<float2*>(red + 4 * kWarps);     // SH only
     float2* sh_tab = sh_amp + 28;
@@ -283,10 +279,11 @@ screen_detect_radix(const __grid_constant__ RunArgs a) {
     const int warp = tid >> 5, lane = tid & 31;
     float2* buf = bufs + ln * F::kBuf;
     const int P = a.n_pup, lo = a.lo;
-    unsigned char* stage = stage_all + warp * 4096;
+    unsigned char* stage = stage_all + warp * kStageBytes;
     uint64_t* bar = bars + warp;
     uint32_t parity = 0;
     if (kTma && lane == 0) mbar_init(bar, 1);
+    const LineSync<S1> sync{ln};
 
     for (int j = tid; j < F::kTwA + F::kTwB; j += THREADS) {
         const int ex = j < F::kTwA ? F::twa_exponent(j) : F::twb_exponent(j - F::kTwA);
@@ -294,6 +291,7 @@ screen_detect_radix(const __grid_constant__ RunArgs a) {
         sincospi(2.0 * (double)ex / (double)N, &s, &c);
         twa[j] = make_float2((float)c, (float)s);
     }
+    if (kTma) fence_proxy_async();            // mbarrier init visible to the async proxy
     __syncthreads();
 
     float2* T = a.scratch + (size_t)blockIdx.x * N * P;
@@ -301,12 +299,12 @@ screen_detect_radix(const __grid_constant__ RunArgs a) {
     const int n1 = N / LPB, n2 = (P + LPB - 1) / LPB;
 
     static_assert(F::k_off_all_even(), "the output sign is taken per thread: k_off must be even");
-    // which of this thread's 16 outputs fall inside the crop [lo, lo+P): the same for every
-    // line of both passes, so it is computed once and tested bit by bit
+    // which of this thread's E outputs fall inside the crop [lo, lo+P): the same for every line
+    // of both passes, so it is computed once and tested bit by bit
     const int kb = F::k_base(u) - lo;
     unsigned need = 0;
 #pragma unroll
-    for (int e = 0; e < 16; ++e)
+    for (int e = 0; e < E; ++e)
         if ((unsigned)(kb + F::k_off(e)) < (unsigned)P) need |= 1u << e;
 
     // Enqueue this warp's input block of iteration `itn` (all lanes call it after a __syncwarp;
@@ -314,8 +312,8 @@ screen_detect_radix(const __grid_constant__ RunArgs a) {
     // no line inside the crop in that iteration.
     auto prefetch = [&](int itn) {
         const bool rows_n = itn < n1;
-        const int line0 = (rows_n ? itn : itn - n1) * LPB + warp * kLinesPerWarp;
         if ((rows_n && !kTmaW) || (!rows_n && !kTmaT)) return;
+        const int line0 = (rows_n ? itn : itn - n1) * LPB + warp * kLinesPerWarp;
         const int nlines = rows_n ? kLinesPerWarp : min(kLinesPerWarp, P - line0);
         if (nlines <= 0 || lane != 0) return;
         const uint32_t bytes = (uint32_t)nlines * N * (rows_n ? 4u : 8u);
@@ -324,10 +322,6 @@ screen_detect_radix(const __grid_constant__ RunArgs a) {
         mbar_expect_tx(bar, bytes);
         bulk_g2s(stage, src, bytes, bar);
     };
-    if (kTma) {
-        fence_proxy_async();                  // mbarrier init visible to the async proxy
-        __syncthreads();
-    }
 
     for (long long pair = blockIdx.x; pair < a.n_pairs; pair += gridDim.x) {
         const unsigned long long g = (unsigned long long)(a.first_pair + pair);
@@ -337,75 +331,73 @@ screen_detect_radix(const __grid_constant__ RunArgs a) {
         for (int it = 0; it < n1 + n2; ++it) {
             const bool rows = it < n1;
             if (it == n1) {
-                if (kTma) fence_proxy_async();        // T was written through the generic proxy
+                if (kTmaT) fence_proxy_async();       // T was written through the generic proxy
                 __syncthreads();                      // every row of T is stored before a column is read
                 if (kTma) prefetch(n1);
             }
             const int line = (rows ? it : it - n1) * LPB + ln;      // r' (pass 1) or c (pass 2)
-            if (!rows) {
-                // last column iteration: warps whose lines all lie beyond the crop have nothing
-                // to do (line barriers involve only the threads of that line)
-                if (line - (ln % kLinesPerWarp) >= P) continue;
-            }
-            float2 v[16];
-            if ((rows && kTmaW) || (!rows && kTmaT)) {
+            // last column iteration: warps whose lines all lie beyond the crop have nothing to do
+            // (line barriers involve only the threads of that line)
+            if (!rows && line - (ln % kLinesPerWarp) >= P) continue;
+
+            float2 v[E];
+            const bool staged = (rows && kTmaW) || (!rows && kTmaT);
+            if (staged) {
                 mbar_wait(bar, parity);
                 parity ^= 1;
-                const int lw = ln % kLinesPerWarp;
-                if (rows) {
-                    const float* ws = reinterpret_cast<const float*>(stage) + lw * N;
-                    float w16[16];
+            }
+            if (rows) {
+                float w[E];
+                if (kTmaW) {
+                    const float* ws = reinterpret_cast<const float*>(stage) + (ln % kLinesPerWarp) * N;
 #pragma unroll
-                    for (int m = 0; m < 16; ++m) w16[m] = ws[u + S1 * m];
+                    for (int m = 0; m < E; ++m) w[m] = ws[u + S1 * m];
                     __syncwarp();
                     if (it + 1 < n1) prefetch(it + 1);
-                    if (RNG) {
+                } else {
+                    const float* wrow = a.weight + (size_t)line * N;
+#pragma unroll
+                    for (int m = 0; m < E; ++m) w[m] = __ldg(wrow + u + S1 * m);
+                }
+                if (RNG) {
+                    // thread (line, u) owns noise blocks t' = u + S1 h of its row: cell j of block h
+                    // is element m = (E/16) j + h (include/fastb.h)
+#pragma unroll
+                    for (int h = 0; h < E / 16; ++h) {
                         uint32_t mr[16], ma[16];
-                        noise_block_fields((uint32_t)(line * S1 + u), g, k0, k1, mr, ma);
+                        noise_block_fields((uint32_t)(line * (N / 16) + u + S1 * h), g, k0, k1, mr, ma);
 #pragma unroll
-                        for (int m = 0; m < 16; ++m) v[m] = weighted_normal_m(mr[m], ma[m], w16[m]);
-                    } else {
-                        const float2* nrow = a.noise + ((size_t)pair * N + line) * N;
-#pragma unroll
-                        for (int m = 0; m < 16; ++m) {
-                            const float2 nz = __ldg(nrow + u + S1 * m);
-                            v[m] = make_float2(nz.x * w16[m], nz.y * w16[m]);
+                        for (int j = 0; j < 16; ++j) {
+                            const int m = (E / 16) * j + h;
+                            v[m] = weighted_normal_m(mr[j], ma[j], w[m]);
                         }
                     }
                 } else {
-                    const float2* ts = reinterpret_cast<const float2*>(stage) + lw * N;
-#pragma unroll
-                    for (int m = 0; m < 16; ++m) v[m] = ts[u + S1 * m];
-                    __syncwarp();
-                    if (it + 1 < n1 + n2) prefetch(it + 1);
-                }
-            } else if (rows) {
-                const float* wrow = a.weight + (size_t)line * N;
-                if (RNG) {
-                    uint32_t mr[16], ma[16];
-                    noise_block_fields((uint32_t)(line * S1 + u), g, k0, k1, mr, ma);
-#pragma unroll
-                    for (int m = 0; m < 16; ++m) v[m] = weighted_normal_m(mr[m], ma[m], __ldg(wrow + u + S1 * m));
-                } else {
                     const float2* nrow = a.noise + ((size_t)pair * N + line) * N;
 #pragma unroll
-                    for (int m = 0; m < 16; ++m) {
-                        const int j = u + S1 * m;
-                        const float2 nz = __ldg(nrow + j);
-                        const float w0 = __ldg(wrow + j);
-                        v[m] = make_float2(nz.x * w0, nz.y * w0);
+                    for (int m = 0; m < E; ++m) {
+                        const float2 nz = __ldg(nrow + u + S1 * m);
+                        v[m] = make_float2(nz.x * w[m], nz.y * w[m]);
                     }
                 }
+            } else if (kTmaT) {
+                const float2* ts = reinterpret_cast<const float2*>(stage) + (ln % kLinesPerWarp) * N;
+#pragma unroll
+                for (int m = 0; m < E; ++m) v[m] = ts[u + S1 * m];
+                __syncwarp();
+                if (it + 1 < n1 + n2) prefetch(it + 1);
             } else {
                 const float2* tcol = T + (size_t)(line < P ? line : 0) * N;
 #pragma unroll
-                for (int m = 0; m < 16; ++m) v[m] = __ldcg(tcol + u + S1 * m);
+                for (int m = 0; m < E; ++m) v[m] = __ldcg(tcol + u + S1 * m);
             }
-            line_fft<LOG2N>(ln, u, v, twa, twb, buf);
+
+            F::run(u, v, twa, twb, buf, sync);
+
             if (rows) {
                 float2* tb = T + ((long long)kb * N + line);  // &T[(k - lo) * N + r'] at k_off = 0
 #pragma unroll
-                for (int e = 0; e < 16; ++e)
+                for (int e = 0; e < E; ++e)
                     if (need & (1u << e)) __stcg(tb + (long long)F::k_off(e) * N, v[e]);
             } else if (line < P) {
                 const float* ub = a.u_t + ((long long)line * P + kb);
@@ -417,7 +409,7 @@ screen_detect_radix(const __grid_constant__ RunArgs a) {
                     for (int i = 0; i < 3; ++i) ex[i] = __ldg(a.sh_ex + i * P + line);
                 }
 #pragma unroll
-                for (int e = 0; e < 16; ++e) {
+                for (int e = 0; e < E; ++e) {
                     if (need & (1u << e)) {
                         const float uu = __ldg(ub + F::k_off(e));
                         if (SH) {
@@ -573,11 +565,10 @@ size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 size_t sh_smem_bytes(bool sh, int n_pup) { return sh ? sizeof(float2) * (28 + (size_t)kShTab * n_pup) : 0; }
 
-template <int LOG2N>
-size_t radix_smem_bytes(bool sh, int n_pup, int threads = kThreads, bool use_tma = false) {
-    using F = LineFFT<LOG2N>;
+template <class F>
+size_t radix_smem_bytes(bool sh, int n_pup, int threads, bool use_tma) {
     const int LPB = threads / F::S1;
-    const size_t tma = (F::S1 <= 32 && use_tma) ? (size_t)(threads / 32) * (4096 + sizeof(uint64_t)) : 0;
+    const size_t tma = (F::S1 <= 32 && use_tma) ? (size_t)(threads / 32) * (32 * F::E * 8 + sizeof(uint64_t)) : 0;
     return sizeof(float2) * ((size_t)F::kTwA + F::kTwB + (size_t)LPB * F::kBuf) + tma +
            sizeof(float) * 4 * (threads / 32) + sh_smem_bytes(sh, n_pup);
 }
@@ -602,27 +593,8 @@ int sm_count(int* out) {
 
 constexpr int kMaxCtasPerSm = 12;
 
-template <int LOG2N>
-int launch_radix(const RunArgs& args, bool rng, int max_grid, cudaStream_t st) {
-    const bool sh = args.sh_weight != nullptr;
-    int threads = radix_threads<LOG2N>();
-    void (*kern)(RunArgs) = nullptr;
-    if (sh) kern = rng ? screen_detect_radix<LOG2N, true, true> : screen_detect_radix<LOG2N, false, true>;
-    else kern = rng ? screen_detect_radix<LOG2N, true, false> : screen_detect_radix<LOG2N, false, false>;
-    bool use_tma = false;
-#ifdef FASTB_TUNE
-    // tuning builds only: FASTB_TMA=1|2|3 routes weights+scratch / scratch only / weights only
-    // through per-warp TMA staging (cp.async.bulk + mbarrier) on the bench path
-    if (rng && !sh) {
-        const char* e = getenv("FASTB_TMA");
-        const int v = e ? atoi(e) : 0;
-        constexpr int T = radix_threads<LOG2N>(), M = radix_min_blocks<LOG2N>();
-        if (v == 1) { kern = screen_detect_radix<LOG2N, true, false, T, M, 1>; use_tma = true; }
-        if (v == 2) { kern = screen_detect_radix<LOG2N, true, false, T, M, 2>; use_tma = true; }
-        if (v == 3) { kern = screen_detect_radix<LOG2N, true, false, T, M, 3>; use_tma = true; }
-    }
-#endif
-    const size_t smem = radix_smem_bytes<LOG2N>(sh, args.n_pup, threads, use_tma);
+int launch_kernel(void (*kern)(RunArgs), const RunArgs& args, int threads, size_t smem, int max_grid,
+                  cudaStream_t st) {
     FASTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     FASTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                                     cudaSharedmemCarveoutMaxShared));
@@ -640,6 +612,57 @@ int launch_radix(const RunArgs& args, bool rng, int max_grid, cudaStream_t st) {
     if (grid > max_grid) grid = max_grid;
     kern<<<(unsigned)grid, threads, smem, st>>>(args);
     return check_launch("screen_detect_radix");
+}
+
+template <int LOG2N, int E>
+int launch_radix_e(const RunArgs& args, bool rng, int max_grid, cudaStream_t st) {
+    using C = RadixCfg<LOG2N, E>;
+    using F = typename C::F;
+    constexpr int T = C::kThreadsPerCta, M = C::kMinBlocks;
+    const bool sh = args.sh_weight != nullptr;
+    void (*kern)(RunArgs) = nullptr;
+    if (sh) kern = rng ? screen_detect_radix<F, true, true, T, M> : screen_detect_radix<F, false, true, T, M>;
+    else kern = rng ? screen_detect_radix<F, true, false, T, M> : screen_detect_radix<F, false, false, T, M>;
+    bool use_tma = false;
+    int threads = T;
+#ifdef FASTB_TUNE
+    // tuning builds only: FASTB_SHAPE=<threads><minblocks> for the 32-element flavour
+    if constexpr (E == 32) {
+        if (rng && !sh) {
+            const char* e = getenv("FASTB_SHAPE");
+            const int v = e ? atoi(e) : 0;
+            if (v == 1284) { kern = screen_detect_radix<F, true, false, 128, 4>; threads = 128; }
+            if (v == 1282) { kern = screen_detect_radix<F, true, false, 128, 2>; threads = 128; }
+            if (v == 2562) { kern = screen_detect_radix<F, true, false, 256, 2>; threads = 256; }
+            if (v == 2561) { kern = screen_detect_radix<F, true, false, 256, 1>; threads = 256; }
+            if (v == 646) { kern = screen_detect_radix<F, true, false, 64, 6>; threads = 64; }
+        }
+    }
+    // tuning builds only: FASTB_TMA=1|2|3 routes weights+scratch / scratch only / weights only
+    // through per-warp TMA staging (cp.async.bulk + mbarrier) on the bench path
+    if constexpr (E == 16) {
+        if (rng && !sh) {
+            const char* e = getenv("FASTB_TMA");
+            const int v = e ? atoi(e) : 0;
+            if (v == 1) { kern = screen_detect_radix<F, true, false, T, M, 1>; use_tma = true; }
+            if (v == 2) { kern = screen_detect_radix<F, true, false, T, M, 2>; use_tma = true; }
+            if (v == 3) { kern = screen_detect_radix<F, true, false, T, M, 3>; use_tma = true; }
+        }
+    }
+#endif
+    return launch_kernel(kern, args, threads, radix_smem_bytes<F>(sh, args.n_pup, threads, use_tma), max_grid, st);
+}
+
+template <int LOG2N>
+int launch_radix(const RunArgs& args, bool rng, int max_grid, cudaStream_t st) {
+#ifdef FASTB_TUNE
+    // tuning builds only: FASTB_E=32 selects the 32-element flavour for N = 512 / 1024
+    if constexpr (LOG2N == 9 || LOG2N == 10) {
+        const char* e = getenv("FASTB_E");
+        if (e && atoi(e) == 32) return launch_radix_e<LOG2N, 32>(args, rng, max_grid, st);
+    }
+#endif
+    return launch_radix_e<LOG2N, radix_default_e<LOG2N>()>(args, rng, max_grid, st);
 }
 
 }  // namespace
