@@ -24,8 +24,28 @@ namespace fastb {
 FASTB_HD float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
+// Complex add / subtract.  On sm_100a the (re, im) pair is handled by ONE packed FP32
+// instruction (add.f32x2 / sub.f32x2 -> SASS FADD2): the kernel is issue-bound, and complex
+// adds are ~30 % of its instructions.  The host build (CPU emulation test) uses scalar code.
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000) && !defined(FASTB_NO_F32X2)
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) {
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;"
+        : "=l"(d)
+        : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
+    return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 csub(float2 a, float2 b) {
+    unsigned long long d;
+    asm("sub.rn.f32x2 %0, %1, %2;"
+        : "=l"(d)
+        : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
+    return *reinterpret_cast<float2*>(&d);
+}
+#else
 FASTB_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 FASTB_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+#endif
 FASTB_HD float2 cmuli(float2 a) { return make_float2(-a.y, a.x); }          // * (+i)
 
 // inverse radix-4: y_k = sum_n x_n i^(n k)
