@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, 'libfastb.so')
 
 MAX_LAYERS = 32
 AO_NOAO, AO_AO, AO_LGSAO = 0, 1, 2
-ALGO_AUTO, ALGO_DIRECT, ALGO_RADIX = 0, 1, 2
+ALGO_AUTO, ALGO_DIRECT, ALGO_RADIX, ALGO_RADIX_PAIR = 0, 1, 2, 3
 
 
 class FastbError(RuntimeError):

@@ -26,6 +26,7 @@ struct RunArgs {
     float inv_usum, sigma_chi;
     const float* weight;      // N*N signed weight
     const float* u_t;         // n_pup*n_pup, transposed: u_t[c*n_pup + r]
+    const float2* u_p;        // line-pair kernel: u_p[cp*n_pup + r] = (U[r][2cp], U[r][2cp+1] or 0)
     const float* chi;         // global-index log-amplitudes or NULL
     const float2* noise;      // n_pairs*N*N or NULL
     float* out_a;
@@ -264,10 +265,11 @@ __global__ void __launch_bounds__(THREADS, MINB) screen_detect_radix(const __gri
     constexpr int kWarps = THREADS / 32;
     constexpr int kStageBytes = 32 * E * 8;
 
+    using Tw = typename F::Tw;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* twa = reinterpret_cast<float2*>(smem_raw);
-    float2* twb = twa + F::kTwA;
-    float2* bufs = twb + F::kTwB;
+    Tw* twa = reinterpret_cast<Tw*>(smem_raw);
+    Tw* twb = twa + F::kTwA;
+    float2* bufs = reinterpret_cast<float2*>(twb + F::kTwB);
     unsigned char* stage_all = reinterpret_cast<unsigned char*>(bufs + LPB * F::kBuf);
     uint64_t* bars = reinterpret_cast<uint64_t*>(stage_all + (kTma ? kWarps * kStageBytes : 0));
     float* red = reinterpret_cast<float*>(bars + (kTma ? kWarps : 0));
@@ -289,7 +291,7 @@ __global__ void __launch_bounds__(THREADS, MINB) screen_detect_radix(const __gri
         const int ex = j < F::kTwA ? F::twa_exponent(j) : F::twb_exponent(j - F::kTwA);
         double s, c;
         sincospi(2.0 * (double)ex / (double)N, &s, &c);
-        twa[j] = make_float2((float)c, (float)s);
+        twa[j] = make_tw((float)c, (float)s, (Tw*)nullptr);
     }
     if (kTma) fence_proxy_async();            // mbarrier init visible to the async proxy
     __syncthreads();
@@ -426,6 +428,183 @@ __global__ void __launch_bounds__(THREADS, MINB) screen_detect_radix(const __gri
     }
 }
 
+// ---- line-PAIR kernel: two adjacent lines per thread group, planar packed FP32 -----------------
+// Same algorithm and results as screen_detect_radix, but every thread carries the same position
+// of TWO adjacent lines (rows 2p, 2p+1 in pass 1; pupil columns 2q, 2q+1 in pass 2) as planar
+// pairs (fft_core.cuh, value type pc), so that all FFT arithmetic and most of Box-Muller are
+// packed FP32 (FADD2 / FMUL2 / FFMA2).  Scratch layout: T4[q][r'] = float4 (re(2q), re(2q+1),
+// im(2q), im(2q+1)), which pass 2 reads with one 128-bit load per element pair.
+__device__ __forceinline__ pc weighted_normal_pair(uint32_t mrA, uint32_t maA, uint32_t mrB, uint32_t maB, float2 w) {
+    const float2 u1 = sub2(bc2(2.0f), make_float2(__uint_as_float(0x3f800000u | mrA), __uint_as_float(0x3f800000u | mrB)));
+    const float2 r2 = mul2(make_float2(__log2f(u1.x), __log2f(u1.y)), bc2(-1.3862943611198906f));
+    float2 rad;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad.x) : "f"(r2.x));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad.y) : "f"(r2.y));
+    rad = mul2(rad, w);
+    const float2 ang = mul2(bc2(6.283185307179586f),
+                            make_float2(__uint_as_float(0x3f800000u | maA), __uint_as_float(0x3f800000u | maB)));
+    float2 sn, cs;
+    __sincosf(ang.x, &sn.x, &cs.x);
+    __sincosf(ang.y, &sn.y, &cs.y);
+    return pc{mul2(rad, cs), mul2(rad, sn)};
+}
+
+// U exp(i s phi) for the two columns (A, B) of a pair and both screens; us = (s_A u_A, s_B u_B)
+__device__ __forceinline__ void accumulate_pair(pc phi, float2 u, float2 us, float (&acc)[4]) {
+    float s, c;
+    __sincosf(phi.re.x, &s, &c);
+    acc[0] = fmaf(u.x, c, acc[0]);
+    acc[1] = fmaf(us.x, s, acc[1]);
+    __sincosf(phi.re.y, &s, &c);
+    acc[0] = fmaf(u.y, c, acc[0]);
+    acc[1] = fmaf(us.y, s, acc[1]);
+    __sincosf(phi.im.x, &s, &c);
+    acc[2] = fmaf(u.x, c, acc[2]);
+    acc[3] = fmaf(us.x, s, acc[3]);
+    __sincosf(phi.im.y, &s, &c);
+    acc[2] = fmaf(u.y, c, acc[2]);
+    acc[3] = fmaf(us.y, s, acc[3]);
+}
+
+template <int LOG2N, bool RNG, bool SH, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) screen_detect_pair(const __grid_constant__ RunArgs a) {
+    using F = LineFFT<LOG2N, pc>;
+    using Tw = typename F::Tw;
+    constexpr int N = F::N, S1 = F::S1, LPB = THREADS / S1;       // LPB line PAIRS per iteration
+    static_assert(THREADS % S1 == 0 && LPB >= 1 && (S1 <= 32 || LPB <= 15), "line/barrier layout");
+    static_assert((N / 2) % LPB == 0, "row pairs per iteration");
+    constexpr int kPairsPerWarp = S1 <= 32 ? 32 / S1 : 1;
+    constexpr int kWarps = THREADS / 32;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Tw* twa = reinterpret_cast<Tw*>(smem_raw);
+    Tw* twb = twa + F::kTwA;
+    float2* bufs = reinterpret_cast<float2*>(twb + F::kTwB);
+    float* red = reinterpret_cast<float*>(bufs + LPB * F::kBuf);
+    float2* sh_amp = reinterpret_cast<float2*>(red + 4 * kWarps);     // SH only
+    float2* sh_tab = sh_amp + 28;
+
+    const int tid = threadIdx.x;
+    const int lp = tid / S1, u = tid % S1;
+    float2* buf = bufs + lp * F::kBuf;
+    const int P = a.n_pup, lo = a.lo, PP = (P + 1) >> 1;             // PP pupil-column pairs
+    const LineSync<S1> sync{lp};
+
+    for (int j = tid; j < F::kTwA + F::kTwB; j += THREADS) {
+        const int ex = j < F::kTwA ? F::twa_exponent(j) : F::twb_exponent(j - F::kTwA);
+        double s, c;
+        sincospi(2.0 * (double)ex / (double)N, &s, &c);
+        twa[j] = make_tw((float)c, (float)s, (Tw*)nullptr);
+    }
+    __syncthreads();
+
+    float4* T4 = reinterpret_cast<float4*>(a.scratch) + (size_t)blockIdx.x * N * PP;
+    const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
+    const int n1 = (N / 2) / LPB, n2 = (PP + LPB - 1) / LPB;
+
+    static_assert(F::k_off_all_even(), "column parity / output sign are taken per thread: k_off must be even");
+    const int kb = F::k_base(u) - lo;          // crop index of this thread's output at k_off = 0
+    unsigned need = 0;
+#pragma unroll
+    for (int e = 0; e < 16; ++e)
+        if ((unsigned)(kb + F::k_off(e)) < (unsigned)P) need |= 1u << e;
+    // output sign (-1)^(r + c) for the even column of a pair; the odd column has the opposite one
+    const float sgn_a = ((F::k_base(u) + lo) & 1) ? -1.f : 1.f;
+    const float2 sgn = make_float2(sgn_a, -sgn_a);
+
+    for (long long pair = blockIdx.x; pair < a.n_pairs; pair += gridDim.x) {
+        const unsigned long long g = (unsigned long long)(a.first_pair + pair);
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        if (SH) sh_prepare(a, pair, sh_amp, sh_tab);   // table visible after the barrier at it == n1
+        for (int it = 0; it < n1 + n2; ++it) {
+            const bool rows = it < n1;
+            if (it == n1) __syncthreads();            // every row of T is stored before a column is read
+            const int pl = (rows ? it : it - n1) * LPB + lp;        // row-pair (pass 1) / column-pair (pass 2)
+            if (!rows && pl - (lp % kPairsPerWarp) >= PP) continue; // warp has no column pair inside the crop
+
+            pc v[16];
+            if (rows) {
+                const int ra = 2 * pl;
+                const float* wa = a.weight + (size_t)ra * N;
+                if (RNG) {
+                    uint32_t mra[16], maa[16], mrb[16], mab[16];
+                    noise_block_fields((uint32_t)(ra * S1 + u), g, k0, k1, mra, maa);
+                    noise_block_fields((uint32_t)((ra + 1) * S1 + u), g, k0, k1, mrb, mab);
+#pragma unroll
+                    for (int m = 0; m < 16; ++m) {
+                        const int j = u + S1 * m;
+                        v[m] = weighted_normal_pair(mra[m], maa[m], mrb[m], mab[m],
+                                                    make_float2(__ldg(wa + j), __ldg(wa + N + j)));
+                    }
+                } else {
+                    const float2* na = a.noise + ((size_t)pair * N + ra) * N;
+#pragma unroll
+                    for (int m = 0; m < 16; ++m) {
+                        const int j = u + S1 * m;
+                        const float2 za = __ldg(na + j), zb = __ldg(na + N + j);
+                        const float2 w = make_float2(__ldg(wa + j), __ldg(wa + N + j));
+                        v[m] = pc{mul2(make_float2(za.x, zb.x), w), mul2(make_float2(za.y, zb.y), w)};
+                    }
+                }
+            } else {
+                const float4* tcol = T4 + (size_t)(pl < PP ? pl : 0) * N;
+                const bool valid_b = 2 * pl + 1 < P;      // odd P: the last pair has no second column
+#pragma unroll
+                for (int m = 0; m < 16; ++m) {
+                    const float4 q = __ldcg(tcol + u + S1 * m);
+                    v[m] = pc{make_float2(q.x, valid_b ? q.y : 0.f), make_float2(q.z, valid_b ? q.w : 0.f)};
+                }
+            }
+
+            F::run(u, v, twa, twb, buf, sync);
+
+            if (rows) {
+                // output k -> crop column c = kb + k_off(e); its pair is c >> 1 and its slot c & 1
+                // (= kb & 1: k_off is even).  Rows 2 pl and 2 pl + 1 are consecutive float4 of T4.
+                float* tb = reinterpret_cast<float*>(T4 + ((long long)(kb >> 1) * N + 2 * pl)) + (kb & 1);
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    if (need & (1u << e)) {
+                        float* q = tb + (long long)(F::k_off(e) / 2) * N * 4;
+                        __stcg(q, v[e].re.x);
+                        __stcg(q + 2, v[e].im.x);
+                        __stcg(q + 4, v[e].re.y);
+                        __stcg(q + 6, v[e].im.y);
+                    }
+                }
+            } else if (pl < PP) {
+                const float2* ub = a.u_p + ((long long)pl * P + kb);
+                float2 exa[3], exb[3];
+                if (SH) {
+                    const int cb = min(2 * pl + 1, P - 1);
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        exa[i] = __ldg(a.sh_ex + i * P + 2 * pl);
+                        exb[i] = __ldg(a.sh_ex + i * P + cb);
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    if (need & (1u << e)) {
+                        const float2 uu = __ldg(ub + F::k_off(e));
+                        if (SH) {
+                            const float2* tabrow = sh_tab + (kb + F::k_off(e)) * kShTab;
+                            const float2 spa = sh_phase(tabrow, exa), spb = sh_phase(tabrow, exb);
+                            pc ph;
+                            ph.re = fma2(sgn, v[e].re, make_float2(spa.x, spb.x));
+                            ph.im = fma2(sgn, v[e].im, make_float2(spa.y, spb.y));
+                            accumulate_pair(ph, uu, uu, acc);
+                        } else {
+                            accumulate_pair(v[e], uu, mul2(uu, sgn), acc);
+                        }
+                    }
+                }
+            }
+        }
+        finish_pair<THREADS>(a, pair, acc, red);
+    }
+}
+
 // ---- general even N: pruned direct DFT (slow path; also used for N not a power of two) ----
 template <bool RNG, bool SH>
 __global__ void __launch_bounds__(kThreads) screen_detect_direct(const __grid_constant__ RunArgs a) {
@@ -544,6 +723,15 @@ __global__ void transpose_u_kernel(const float* __restrict__ U, int P, float* __
     u_t[(size_t)c * P + r] = U[i];
 }
 
+// u_p[(q * P + r) * 2 + j] = U[r][2q + j] (0 beyond the last column): U for the line-pair kernel
+__global__ void pair_u_kernel(const float* __restrict__ U, int P, float* __restrict__ u_p) {
+    const int PP = (P + 1) >> 1;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= PP * P * 2) return;
+    const int j = i & 1, r = (i >> 1) % P, q = (i >> 1) / P, c = 2 * q + j;
+    u_p[i] = c < P ? U[(size_t)r * P + c] : 0.f;
+}
+
 __global__ void rng_dump_kernel(unsigned long long seed, unsigned long long g, int N, float2* tile,
                                 long long chi_first, long long chi_count, float* chi) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -569,7 +757,7 @@ template <class F>
 size_t radix_smem_bytes(bool sh, int n_pup, int threads, bool use_tma) {
     const int LPB = threads / F::S1;
     const size_t tma = (F::S1 <= 32 && use_tma) ? (size_t)(threads / 32) * (32 * F::E * 8 + sizeof(uint64_t)) : 0;
-    return sizeof(float2) * ((size_t)F::kTwA + F::kTwB + (size_t)LPB * F::kBuf) + tma +
+    return sizeof(typename F::Tw) * ((size_t)F::kTwA + F::kTwB) + sizeof(float2) * (size_t)LPB * F::kBuf + tma +
            sizeof(float) * 4 * (threads / 32) + sh_smem_bytes(sh, n_pup);
 }
 
@@ -653,6 +841,34 @@ int launch_radix_e(const RunArgs& args, bool rng, int max_grid, cudaStream_t st)
     return launch_kernel(kern, args, threads, radix_smem_bytes<F>(sh, args.n_pup, threads, use_tma), max_grid, st);
 }
 
+// line-pair kernel: N <= 256: 128 threads x 5 CTAs/SM (96 registers); above: 256 x 2 (128 registers)
+template <int LOG2N>
+int launch_pair(const RunArgs& args, bool rng, int max_grid, cudaStream_t st) {
+    using F = LineFFT<LOG2N, pc>;
+    constexpr int T = LOG2N <= 8 ? 128 : 256, M = LOG2N <= 8 ? 5 : 2;
+    const bool sh = args.sh_weight != nullptr;
+    void (*kern)(RunArgs) = nullptr;
+    if (sh) kern = rng ? screen_detect_pair<LOG2N, true, true, T, M> : screen_detect_pair<LOG2N, false, true, T, M>;
+    else kern = rng ? screen_detect_pair<LOG2N, true, false, T, M> : screen_detect_pair<LOG2N, false, false, T, M>;
+    int threads = T;
+#ifdef FASTB_TUNE
+    if (rng && !sh) {      // tuning builds only: FASTB_PAIR_SHAPE=<threads><min blocks>
+        const char* e = getenv("FASTB_PAIR_SHAPE");
+        const int v = e ? atoi(e) : 0;
+        if (v == 1284) { kern = screen_detect_pair<LOG2N, true, false, 128, 4>; threads = 128; }
+        if (v == 1285) { kern = screen_detect_pair<LOG2N, true, false, 128, 5>; threads = 128; }
+        if constexpr (LOG2N >= 7) {
+            if (v == 2562) { kern = screen_detect_pair<LOG2N, true, false, 256, 2>; threads = 256; }
+        }
+        if constexpr (LOG2N <= 9) {
+            if (v == 648) { kern = screen_detect_pair<LOG2N, true, false, 64, 8>; threads = 64; }
+            if (v == 646) { kern = screen_detect_pair<LOG2N, true, false, 64, 6>; threads = 64; }
+        }
+    }
+#endif
+    return launch_kernel(kern, args, threads, radix_smem_bytes<F>(sh, args.n_pup, threads, false), max_grid, st);
+}
+
 template <int LOG2N>
 int launch_radix(const RunArgs& args, bool rng, int max_grid, cudaStream_t st) {
 #ifdef FASTB_TUNE
@@ -678,9 +894,9 @@ static int validate_run(const FastbRunParams* p) {
                   p->lo, p->lo + p->n_pup);
     FASTB_REQUIRE(p->n_pairs >= 0 && p->first_pair >= 0, "fastb_screen_detect: negative pair range");
     FASTB_REQUIRE(p->pairs_per_chunk > 0, "fastb_screen_detect: pairs_per_chunk must be > 0");
-    FASTB_REQUIRE(p->algo >= FASTB_ALGO_AUTO && p->algo <= FASTB_ALGO_RADIX, "fastb_screen_detect: bad algo");
+    FASTB_REQUIRE(p->algo >= FASTB_ALGO_AUTO && p->algo <= FASTB_ALGO_RADIX_PAIR, "fastb_screen_detect: bad algo");
     FASTB_REQUIRE(p->u_sum != 0.0, "fastb_screen_detect: u_sum is zero");
-    if (p->algo == FASTB_ALGO_RADIX && !radix_ok(p->n)) {
+    if ((p->algo == FASTB_ALGO_RADIX || p->algo == FASTB_ALGO_RADIX_PAIR) && !radix_ok(p->n)) {
         set_error("fastb_screen_detect: radix path needs N = 64..2048 power of two, got %d", p->n);
         return FASTB_ERR_UNSUPPORTED;
     }
@@ -698,8 +914,8 @@ extern "C" int64_t fastb_screen_detect_workspace_bytes(const FastbRunParams* p) 
     long long grid = (long long)sms * kMaxCtasPerSm;
     if (grid > p->n_pairs) grid = p->n_pairs;
     if (grid < 1) grid = 1;
-    const size_t ut = align_up(sizeof(float) * (size_t)p->n_pup * p->n_pup, 256);
-    return (int64_t)(ut + (size_t)grid * p->n * p->n_pup * sizeof(float2));
+    const size_t ut = align_up(sizeof(float) * (size_t)(p->n_pup + 1) * p->n_pup, 256);
+    return (int64_t)(ut + (size_t)grid * p->n * (p->n_pup + 1) * sizeof(float2));
 }
 
 extern "C" int fastb_screen_detect(const FastbRunParams* p, const float* d_weight, const float* d_U,
@@ -713,8 +929,9 @@ extern "C" int fastb_screen_detect(const FastbRunParams* p, const float* d_weigh
                   "fastb_screen_detect: d_weight must be 16-byte and d_workspace 256-byte aligned");
     if (p->n_pairs == 0) return FASTB_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t ut = align_up(sizeof(float) * (size_t)p->n_pup * p->n_pup, 256);
-    const size_t slot = (size_t)p->n * p->n_pup * sizeof(float2);
+    // [U table: transposed (P*P) or pair-interleaved ((P+1)*P) | scratch slots of N*(P+1) complex]
+    const size_t ut = align_up(sizeof(float) * (size_t)(p->n_pup + 1) * p->n_pup, 256);
+    const size_t slot = (size_t)p->n * (p->n_pup + 1) * sizeof(float2);
     FASTB_REQUIRE(workspace_bytes >= (int64_t)(ut + slot), "fastb_screen_detect: workspace too small (%lld B)",
                   (long long)workspace_bytes);
     long long max_grid = (long long)(((size_t)workspace_bytes - ut) / slot);
@@ -733,6 +950,7 @@ extern "C" int fastb_screen_detect(const FastbRunParams* p, const float* d_weigh
     a.sigma_chi = p->sigma_chi;
     a.weight = d_weight;
     a.u_t = (const float*)d_workspace;
+    a.u_p = (const float2*)d_workspace;
     a.chi = d_chi;
     a.noise = (const float2*)d_noise;
     a.out_a = d_out_a;
@@ -754,11 +972,28 @@ extern "C" int fastb_screen_detect(const FastbRunParams* p, const float* d_weigh
         a.sh_mean = (const float2*)sh->d_mean;
     }
 
+    const bool rng = d_noise == nullptr;
+    // AUTO picks the one-line radix kernel: the line-pair kernel executes 22 % fewer instructions
+    // but measured 4-10 % slower in its best shape (profiles/experiments_r01.txt)
+    const bool use_pair = p->algo == FASTB_ALGO_RADIX_PAIR;
+    if (use_pair) {
+        const int cnt = ((p->n_pup + 1) / 2) * p->n_pup * 2;
+        pair_u_kernel<<<(cnt + 255) / 256, 256, 0, st>>>(d_U, p->n_pup, (float*)d_workspace);
+        if ((rc = check_launch("pair_u_kernel"))) return rc;
+        switch (p->n) {
+            case 64: return launch_pair<6>(a, rng, (int)max_grid, st);
+            case 128: return launch_pair<7>(a, rng, (int)max_grid, st);
+            case 256: return launch_pair<8>(a, rng, (int)max_grid, st);
+            case 512: return launch_pair<9>(a, rng, (int)max_grid, st);
+            case 1024: return launch_pair<10>(a, rng, (int)max_grid, st);
+            case 2048: return launch_pair<11>(a, rng, (int)max_grid, st);
+            default: break;
+        }
+    }
     const int pp = p->n_pup * p->n_pup;
     transpose_u_kernel<<<(pp + 255) / 256, 256, 0, st>>>(d_U, p->n_pup, (float*)d_workspace);
     if ((rc = check_launch("transpose_u_kernel"))) return rc;
 
-    const bool rng = d_noise == nullptr;
     const bool use_radix = p->algo == FASTB_ALGO_RADIX || (p->algo == FASTB_ALGO_AUTO && radix_ok(p->n));
     if (use_radix) {
         switch (p->n) {
@@ -806,8 +1041,8 @@ extern "C" int fastb_screens_crop(const FastbRunParams* p, const float* d_weight
     FASTB_REQUIRE(d_weight && d_phs && d_workspace, "fastb_screens_crop: NULL pointer");
     if (p->n_pairs == 0) return FASTB_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t ut = align_up(sizeof(float) * (size_t)p->n_pup * p->n_pup, 256);
-    const size_t slot = (size_t)p->n * p->n_pup * sizeof(float2);
+    const size_t ut = align_up(sizeof(float) * (size_t)(p->n_pup + 1) * p->n_pup, 256);
+    const size_t slot = (size_t)p->n * (p->n_pup + 1) * sizeof(float2);
     FASTB_REQUIRE(workspace_bytes >= (int64_t)(ut + slot), "fastb_screens_crop: workspace too small");
     long long max_grid = (long long)(((size_t)workspace_bytes - ut) / slot);
     RunArgs a = {};

@@ -152,7 +152,11 @@ int64_t fastb_pupil_filter_workspace_bytes(int32_t n);
 enum {
     FASTB_ALGO_AUTO = 0,
     FASTB_ALGO_DIRECT = 1,          /* pruned direct DFT, any even N */
-    FASTB_ALGO_RADIX = 2            /* register radix-16 FFT, N = 64..2048 power of two */
+    FASTB_ALGO_RADIX = 2,           /* register radix-16 FFT, one line per thread group, N = 64..2048
+                                       power of two; what AUTO selects for those sizes */
+    FASTB_ALGO_RADIX_PAIR = 3       /* same FFT on two adjacent lines per thread group, all arithmetic
+                                       in packed FP32 (FADD2/FMUL2/FFMA2): fewer instructions, but
+                                       measured slower than RADIX on B200; kept as a cross-check */
 };
 
 typedef struct FastbRunParams {

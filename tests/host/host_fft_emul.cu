@@ -1,6 +1,8 @@
 // CPU emulation of fast_b200/csrc/fft_core.cuh: runs the exact per-thread phases of the line
-// FFT sequentially (threads emulated between sync points) and checks against a direct
-// float64 DFT.  Built and run by tests/test_host_fft.py (no GPU needed).
+// FFT sequentially (all threads of a line between two sync points, then the next phase) and
+// checks against a direct float64 DFT -- for the one-line value type (float2), the line-pair
+// type (pc: two different lines, planar shared-memory layout) and the 32-elements-per-thread
+// tuning flavour.  Built and run by tests/test_host_fft.py (no GPU needed).
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -10,31 +12,78 @@
 
 using namespace fastb;
 
-template <int LOG2N>
+static float2 lane(const float2& v, int) { return v; }
+static float2 lane(const pc& v, int l) { return l == 0 ? make_float2(v.re.x, v.im.x) : make_float2(v.re.y, v.im.y); }
+static void set_lanes(float2& v, const float2& a, const float2&) { v = a; }
+static void set_lanes(pc& v, const float2& a, const float2& b) {
+    v.re = make_float2(a.x, b.x);
+    v.im = make_float2(a.y, b.y);
+}
+
+template <class Tw>
+static std::vector<Tw> table(int n, int N, int (*expo)(int)) {
+    std::vector<Tw> t(n + 1);
+    for (int i = 0; i < n; ++i) {
+        const int ex = expo(i);
+        t[i] = make_tw((float)cos(2.0 * M_PI * ex / N), (float)sin(2.0 * M_PI * ex / N), (Tw*)nullptr);
+    }
+    return t;
+}
+
+// compare the outputs X[l][k] of `lines` lines with the direct DFT of x[l]
+static double check(const std::vector<float2> (&x)[2], const std::vector<float2> (&X)[2],
+                    const std::vector<int>& seen, int lines, const char* label) {
+    const int N = (int)x[0].size();
+    for (int k = 0; k < N; ++k)
+        if (seen[k] != 1) {
+            printf("%s: output %d produced %d times\n", label, k, seen[k]);
+            return 1e9;
+        }
+    double worst = 0, scale = 0;
+    for (int l = 0; l < lines; ++l)
+        for (int k = 0; k < N; ++k) {
+            double re = 0, im = 0;
+            for (int n = 0; n < N; ++n) {
+                const double ang = 2.0 * M_PI * (double)(((long long)n * k) % N) / N;
+                re += x[l][n].x * cos(ang) - x[l][n].y * sin(ang);
+                im += x[l][n].x * sin(ang) + x[l][n].y * cos(ang);
+            }
+            worst = fmax(worst, hypot(X[l][k].x - re, X[l][k].y - im));
+            scale = fmax(scale, hypot(re, im));
+        }
+    printf("%s  max_err/max_abs=%.3e\n", label, worst / scale);
+    return worst / scale;
+}
+
+template <int LOG2N, class V>
 double run_one(unsigned seed) {
-    using F = LineFFT<LOG2N>;
-    constexpr int N = F::N;
-    std::vector<float2> x(N), twa(F::kTwA), twb(F::kTwB + 1), buf(F::kBuf), X(N);
+    using F = LineFFT<LOG2N, V>;
+    using Tw = typename F::Tw;
+    constexpr int N = F::N, L = F::kLines;
+    std::vector<float2> x[2], X[2];
     std::vector<int> seen(N, 0);
     srand(seed);
-    for (int i = 0; i < N; ++i) {
-        x[i] = make_float2((float)rand() / RAND_MAX - 0.5f, (float)rand() / RAND_MAX - 0.5f);
+    for (int l = 0; l < 2; ++l) {
+        x[l].resize(N);
+        X[l].resize(N);
+        for (int i = 0; i < N; ++i)
+            x[l][i] = make_float2((float)rand() / RAND_MAX - 0.5f, (float)rand() / RAND_MAX - 0.5f);
     }
-    for (int i = 0; i < F::kTwA; ++i) {
-        const int ex = F::twa_exponent(i);
-        twa[i] = make_float2((float)cos(2.0 * M_PI * ex / N), (float)sin(2.0 * M_PI * ex / N));
-    }
-    for (int i = 0; i < F::kTwB; ++i) {
-        const int ex = F::twb_exponent(i);
-        twb[i] = make_float2((float)cos(2.0 * M_PI * ex / N), (float)sin(2.0 * M_PI * ex / N));
-    }
-    float2 v[16];
+    std::vector<Tw> twa = table<Tw>(F::kTwA, N, F::twa_exponent), twb = table<Tw>(F::kTwB, N, F::twb_exponent);
+    std::vector<float2> buf(F::kBuf);
+    std::vector<V> keep((size_t)16 * F::S1);
+    V v[16];
+    auto emit = [&](int u) {
+        for (int e = 0; e < 16; ++e) {
+            for (int l = 0; l < L; ++l) X[l][F::k_out(u, e)] = lane(v[e], l);
+            seen[F::k_out(u, e)]++;
+        }
+    };
     for (int t = 0; t < F::S1; ++t) {
-        for (int m = 0; m < 16; ++m) v[m] = x[F::n_in(t, m)];
+        for (int m = 0; m < 16; ++m) set_lanes(v[m], x[0][F::n_in(t, m)], x[1][F::n_in(t, m)]);
         F::phase_a(t, v, twa.data(), buf.data());
     }
     if (F::kThree) {
-        std::vector<float2> keep(16 * F::S1);
         for (int u = 0; u < F::S1; ++u) {
             F::phase_b(u, v, twb.data(), buf.data());
             for (int e = 0; e < 16; ++e) keep[u * 16 + e] = v[e];
@@ -46,82 +95,70 @@ double run_one(unsigned seed) {
             }
             for (int u = 0; u < F::S1; ++u) {
                 F::phase_c(u, v, buf.data());
-                for (int e = 0; e < 16; ++e) { X[F::k_out(u, e)] = v[e]; seen[F::k_out(u, e)]++; }
+                emit(u);
             }
         } else {
-            for (int u = 0; u < F::S1; ++u)
-                for (int e = 0; e < 16; ++e) { X[F::k_out(u, e)] = keep[u * 16 + e]; seen[F::k_out(u, e)]++; }
+            for (int u = 0; u < F::S1; ++u) {
+                for (int e = 0; e < 16; ++e) v[e] = keep[u * 16 + e];
+                emit(u);
+            }
         }
     } else {
         for (int u = 0; u < F::S1; ++u) {
             F::phase_c(u, v, buf.data());
-            for (int e = 0; e < 16; ++e) { X[F::k_out(u, e)] = v[e]; seen[F::k_out(u, e)]++; }
+            emit(u);
         }
     }
-    double worst = 0, scale = 0;
-    for (int k = 0; k < N; ++k) {
-        if (seen[k] != 1) { printf("N=%d: output %d produced %d times\n", N, k, seen[k]); return 1e9; }
-        double re = 0, im = 0;
-        for (int n = 0; n < N; ++n) {
-            const double ang = 2.0 * M_PI * (double)(((long long)n * k) % N) / N;
-            re += x[n].x * cos(ang) - x[n].y * sin(ang);
-            im += x[n].x * sin(ang) + x[n].y * cos(ang);
-        }
-        worst = fmax(worst, hypot(X[k].x - re, X[k].y - im));
-        scale = fmax(scale, hypot(re, im));
-    }
-    printf("N=%d S1=%d S2=%d SF=%d buf=%d  max_err/max_abs=%.3e\n", N, F::S1, F::S2, F::SF, F::kBuf, worst / scale);
-    return worst / scale;
+    char label[96];
+    snprintf(label, sizeof label, "N=%d lines=%d S1=%d S2=%d SF=%d buf=%d", N, L, F::S1, F::S2, F::SF, F::kBuf);
+    return check(x, X, seen, L, label);
 }
 
 template <int LOG2N>
 double run_32(unsigned seed) {
     using F = LineFFT32<LOG2N>;
     constexpr int N = F::N;
-    std::vector<float2> x(N), twa(F::kTwA), buf(F::kBuf), X(N);
+    std::vector<float2> x[2], X[2];
     std::vector<int> seen(N, 0);
     srand(seed);
+    x[0].resize(N);
+    X[0].resize(N);
     for (int i = 0; i < N; ++i)
-        x[i] = make_float2((float)rand() / RAND_MAX - 0.5f, (float)rand() / RAND_MAX - 0.5f);
-    for (int i = 0; i < F::kTwA; ++i) {
-        const int ex = F::twa_exponent(i);
-        twa[i] = make_float2((float)cos(2.0 * M_PI * ex / N), (float)sin(2.0 * M_PI * ex / N));
-    }
+        x[0][i] = make_float2((float)rand() / RAND_MAX - 0.5f, (float)rand() / RAND_MAX - 0.5f);
+    std::vector<float2> twa = table<float2>(F::kTwA, N, F::twa_exponent), buf(F::kBuf);
     float2 v[32];
     for (int t = 0; t < F::S1; ++t) {
-        for (int m = 0; m < 32; ++m) v[m] = x[F::n_in(t, m)];
+        for (int m = 0; m < 32; ++m) v[m] = x[0][F::n_in(t, m)];
         F::phase_a(t, v, twa.data(), buf.data());
     }
     for (int u = 0; u < F::S1; ++u) {
         F::phase_b(u, v, buf.data());
-        for (int e = 0; e < 32; ++e) { X[F::k_out(u, e)] = v[e]; seen[F::k_out(u, e)]++; }
-    }
-    double worst = 0, scale = 0;
-    for (int k = 0; k < N; ++k) {
-        if (seen[k] != 1) { printf("N=%d (E=32): output %d produced %d times\n", N, k, seen[k]); return 1e9; }
-        double re = 0, im = 0;
-        for (int n = 0; n < N; ++n) {
-            const double ang = 2.0 * M_PI * (double)(((long long)n * k) % N) / N;
-            re += x[n].x * cos(ang) - x[n].y * sin(ang);
-            im += x[n].x * sin(ang) + x[n].y * cos(ang);
+        for (int e = 0; e < 32; ++e) {
+            X[0][F::k_out(u, e)] = v[e];
+            seen[F::k_out(u, e)]++;
         }
-        worst = fmax(worst, hypot(X[k].x - re, X[k].y - im));
-        scale = fmax(scale, hypot(re, im));
     }
-    printf("N=%d E=32 S1=%d buf=%d  max_err/max_abs=%.3e\n", N, F::S1, F::kBuf, worst / scale);
-    return worst / scale;
+    char label[96];
+    snprintf(label, sizeof label, "N=%d E=32 S1=%d buf=%d", N, F::S1, F::kBuf);
+    return check(x, X, seen, 1, label);
 }
 
 int main() {
     double w = 0;
+    w = fmax(w, run_one<6, float2>(1));
+    w = fmax(w, run_one<7, float2>(2));
+    w = fmax(w, run_one<8, float2>(3));
+    w = fmax(w, run_one<9, float2>(4));
+    w = fmax(w, run_one<10, float2>(5));
+    w = fmax(w, run_one<11, float2>(6));
+    w = fmax(w, run_one<6, pc>(11));
+    w = fmax(w, run_one<7, pc>(12));
+    w = fmax(w, run_one<8, pc>(13));
+    w = fmax(w, run_one<9, pc>(14));
+    w = fmax(w, run_one<10, pc>(15));
+    w = fmax(w, run_one<11, pc>(16));
     w = fmax(w, run_32<9>(7));
     w = fmax(w, run_32<10>(8));
-    w = fmax(w, run_one<6>(1));
-    w = fmax(w, run_one<7>(2));
-    w = fmax(w, run_one<8>(3));
-    w = fmax(w, run_one<9>(4));
-    w = fmax(w, run_one<10>(5));
-    w = fmax(w, run_one<11>(6));
     printf("worst %.3e\n", w);
     return w < 2e-6 ? 0 : 1;
 }

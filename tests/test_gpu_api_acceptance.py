@@ -168,7 +168,7 @@ def test_pupil_as_large_as_the_grid_and_one_pixel_pupil(fast):
         rp.n, rp.n_pup, rp.lo, rp.n_pairs, rp.pairs_per_chunk, rp.seed = N, P, lo, 6, 3, 11
         rp.u_sum, rp.sigma_chi = float(P * P), 0.0
         outs = []
-        for algo in (lib.ALGO_RADIX, lib.ALGO_DIRECT):
+        for algo in (lib.ALGO_RADIX_PAIR, lib.ALGO_RADIX, lib.ALGO_DIRECT):
             rp.algo = algo
             ws = torch.empty(lib.screen_detect_workspace_bytes(rp), dtype=torch.uint8, device=dev)
             a = torch.empty(6, dtype=torch.float32, device=dev)
@@ -176,7 +176,8 @@ def test_pupil_as_large_as_the_grid_and_one_pixel_pupil(fast):
             lib.screen_detect(rp, weight, U, a, b, ws)
             outs.append(torch.cat([a, b]).cpu().numpy())
         assert np.isfinite(outs[0]).all() and (outs[0] <= 1 + 1e-5).all()
-        np.testing.assert_allclose(outs[0], outs[1], rtol=2e-4)
+        np.testing.assert_allclose(outs[0], outs[2], rtol=2e-4)
+        np.testing.assert_allclose(outs[1], outs[2], rtol=2e-4)
         if P == 1:
             np.testing.assert_allclose(outs[0], 1.0, rtol=1e-6)      # |exp(i phi)|^2 = 1
 
@@ -199,7 +200,8 @@ def test_largest_radix_grid_2048(fast):
     p = dict(fast.configs.c5(niter=2, nchunks=1, seed=3), NPXLS=2048, DX=0.0025, LOGLEVEL='ERROR')
     sim = fast.Fast(p)
     assert sim.Npxls == 2048 and sim.Npxls_pup == 322
-    a1, b1 = sim.screen_detect(0, 1, algo=fast._lib.ALGO_RADIX)
     a2, b2 = sim.screen_detect(0, 1, algo=fast._lib.ALGO_DIRECT)
-    np.testing.assert_allclose(a1.cpu().numpy(), a2.cpu().numpy(), rtol=2e-4)
-    np.testing.assert_allclose(b1.cpu().numpy(), b2.cpu().numpy(), rtol=2e-4)
+    for algo in (fast._lib.ALGO_RADIX, fast._lib.ALGO_RADIX_PAIR):
+        a1, b1 = sim.screen_detect(0, 1, algo=algo)
+        np.testing.assert_allclose(a1.cpu().numpy(), a2.cpu().numpy(), rtol=2e-4)
+        np.testing.assert_allclose(b1.cpu().numpy(), b2.cpu().numpy(), rtol=2e-4)

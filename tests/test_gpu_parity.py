@@ -117,15 +117,44 @@ def test_device_rng_run_matches_oracle(fast, name, npairs):
     assert np.max(np.abs(got - want) / np.abs(want)) < 5e-4   # noise itself differs by ~1e-6 (MUFU)
 
 
-@pytest.mark.parametrize('name', ['mini_ao', 'c2', 'c4', 'c5'])
-def test_radix_and_direct_paths_agree(fast, name):
+@pytest.mark.parametrize('name', ['mini_ao', 'mini_coherent', 'c2', 'c4', 'c5'])
+def test_radix_pair_and_direct_paths_agree(fast, name):
+    """Three independent device implementations of K2 -- one-line radix kernel (the default),
+    line-pair packed-FP32 radix kernel, pruned direct DFT -- give the same realisations."""
     g, p = load_golden(name)
     sim = fast.Fast(dict(p, NITER=8, NCHUNKS=1, SEED=5))
-    a1, b1 = sim.screen_detect(3, 4, algo=fast._lib.ALGO_RADIX)
-    a2, b2 = sim.screen_detect(3, 4, algo=fast._lib.ALGO_DIRECT)
-    for x, y in ((a1, a2), (b1, b2)):
-        x, y = x.cpu().numpy(), y.cpu().numpy()
-        assert np.max(np.abs(x - y) / np.abs(y)) < 1e-4
+    res = {}
+    for algo in (fast._lib.ALGO_RADIX_PAIR, fast._lib.ALGO_RADIX, fast._lib.ALGO_DIRECT, fast._lib.ALGO_AUTO):
+        a, b = sim.screen_detect(3, 4, algo=algo)
+        res[algo] = np.concatenate([a.cpu().numpy(), b.cpu().numpy()])
+    ref = res[fast._lib.ALGO_DIRECT]
+    for algo, x in res.items():
+        assert np.max(np.abs(x - ref) / np.abs(ref)) < 1e-4, algo
+    np.testing.assert_array_equal(res[fast._lib.ALGO_AUTO], res[fast._lib.ALGO_RADIX])
+
+
+@pytest.mark.parametrize('N,P', [(64, 21), (128, 45), (256, 83), (512, 101), (1024, 7), (2048, 33)])
+def test_odd_pupil_widths_on_both_radix_kernels(fast, N, P):
+    """Odd n_pup: the last column pair of the line-pair kernel has a single valid column."""
+    lib = fast._lib
+    dev = torch.device('cuda')
+    gen = torch.Generator(device='cuda').manual_seed(N + P)
+    w = torch.rand(N, N, dtype=torch.float64, device=dev, generator=gen) * 1e-5
+    weight = lib.make_weight(w, 1.5)
+    U = torch.rand(P, P, dtype=torch.float32, device=dev, generator=gen)
+    lo = (N - P) // 2
+    outs = []
+    for algo in (lib.ALGO_RADIX_PAIR, lib.ALGO_RADIX, lib.ALGO_DIRECT):
+        rp = lib.RunParams()
+        rp.n, rp.n_pup, rp.lo, rp.n_pairs, rp.pairs_per_chunk, rp.seed, rp.algo = N, P, lo, 3, 3, 99, algo
+        rp.u_sum, rp.sigma_chi = float(U.sum()), 0.05
+        ws = torch.empty(lib.screen_detect_workspace_bytes(rp), dtype=torch.uint8, device=dev)
+        a = torch.empty(3, dtype=torch.float32, device=dev)
+        b = torch.empty(3, dtype=torch.float32, device=dev)
+        lib.screen_detect(rp, weight, U, a, b, ws)
+        outs.append(torch.cat([a, b]).cpu().numpy())
+    np.testing.assert_allclose(outs[0], outs[2], rtol=2e-4)
+    np.testing.assert_allclose(outs[1], outs[2], rtol=2e-4)
 
 
 def test_results_do_not_depend_on_launch_split(fast):
@@ -253,10 +282,11 @@ def test_subharm_device_rng_matches_oracle(fast, name):
     assert np.max(np.abs(got - want) / np.abs(want)) < 5e-4
     # radix and direct paths agree with the sub-harmonic term as well
     if sim.Npxls == 64:
-        a1, b1 = sim.screen_detect(0, 4, algo=fast._lib.ALGO_RADIX)
         a2, b2 = sim.screen_detect(0, 4, algo=fast._lib.ALGO_DIRECT)
-        np.testing.assert_allclose(a1.cpu().numpy(), a2.cpu().numpy(), rtol=1e-4)
-        np.testing.assert_allclose(b1.cpu().numpy(), b2.cpu().numpy(), rtol=1e-4)
+        for algo in (fast._lib.ALGO_RADIX, fast._lib.ALGO_RADIX_PAIR):
+            a1, b1 = sim.screen_detect(0, 4, algo=algo)
+            np.testing.assert_allclose(a1.cpu().numpy(), a2.cpu().numpy(), rtol=1e-4)
+            np.testing.assert_allclose(b1.cpu().numpy(), b2.cpu().numpy(), rtol=1e-4)
 
 
 def test_elevation_sweep_matches_individual_runs(fast):

@@ -16,4 +16,4 @@ def test_line_fft_index_algebra(tmp_path):
                    check=True, capture_output=True)
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout
-    assert out.stdout.count('max_err') == 8
+    assert out.stdout.count('max_err') == 14
