@@ -7,6 +7,7 @@
 #include <stdarg.h>
 
 #include "../../include/fastb.h"
+#include "fft_core.cuh"
 
 namespace fastb {
 
@@ -64,9 +65,9 @@ __device__ __forceinline__ float2 weighted_normal_m(uint32_t mr, uint32_t ma, fl
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(-1.3862943611198906f * __log2f(u1)));
     rad *= w;
     const float ang = 6.283185307179586f * __uint_as_float(0x3f800000u | ma);
-    float s, c;
-    __sincosf(ang, &s, &c);
-    return make_float2(rad * c, rad * s);
+    float2 cs;
+    __sincosf(ang, &cs.y, &cs.x);
+    return mul2(cs, bc2(rad));            // (rad cos, rad sin): one FMUL2 with a broadcast operand
 }
 
 // top 23 bits of each word (used by the chi and sub-harmonic streams)

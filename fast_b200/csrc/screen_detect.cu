@@ -40,7 +40,16 @@ struct RunArgs {
     const float2* sh_ey;      // 3*n_pup
     const float2* sh_mean;    // 27
     float* phs;               // direct kernel only: write the cropped screens instead of detecting
+#ifdef FASTB_TUNE
+    int dbg;                  // timing experiments (results wrong): 1 no scratch stores, 2 no weight
+                              // loads, 4 no scratch loads, 8 no detector loads, 16 no noise
+#endif
 };
+#ifdef FASTB_TUNE
+#define FASTB_DBG(a, bit) ((a).dbg & (bit))
+#else
+#define FASTB_DBG(a, bit) 0
+#endif
 
 // ---- sub-harmonic term (include/fastb.h FastbSubharm) ------------------------------------
 // Per pair: 27 amplitudes -> per pupil row a table of 7 complex numbers
@@ -359,9 +368,12 @@ __global__ void __launch_bounds__(THREADS, MINB) screen_detect_radix(const __gri
                 } else {
                     const float* wrow = a.weight + (size_t)line * N;
 #pragma unroll
-                    for (int m = 0; m < E; ++m) w[m] = __ldg(wrow + u + S1 * m);
+                    for (int m = 0; m < E; ++m) w[m] = FASTB_DBG(a, 2) ? 1.f + m : __ldg(wrow + u + S1 * m);
                 }
-                if (RNG) {
+                if (RNG && FASTB_DBG(a, 16)) {
+#pragma unroll
+                    for (int m = 0; m < E; ++m) v[m] = make_float2(w[m], w[m] * u);
+                } else if (RNG) {
                     // thread (line, u) owns noise blocks t' = u + S1 h of its row: cell j of block h
                     // is element m = (E/16) j + h (include/fastb.h)
 #pragma unroll
@@ -391,7 +403,7 @@ __global__ void __launch_bounds__(THREADS, MINB) screen_detect_radix(const __gri
             } else {
                 const float2* tcol = T + (size_t)(line < P ? line : 0) * N;
 #pragma unroll
-                for (int m = 0; m < E; ++m) v[m] = __ldcg(tcol + u + S1 * m);
+                for (int m = 0; m < E; ++m) v[m] = FASTB_DBG(a, 4) ? make_float2(m, u) : __ldcg(tcol + u + S1 * m);
             }
 
             F::run(u, v, twa, twb, buf, sync);
@@ -400,7 +412,7 @@ __global__ void __launch_bounds__(THREADS, MINB) screen_detect_radix(const __gri
                 float2* tb = T + ((long long)kb * N + line);  // &T[(k - lo) * N + r'] at k_off = 0
 #pragma unroll
                 for (int e = 0; e < E; ++e)
-                    if (need & (1u << e)) __stcg(tb + (long long)F::k_off(e) * N, v[e]);
+                    if ((need & (1u << e)) && !FASTB_DBG(a, 1)) __stcg(tb + (long long)F::k_off(e) * N, v[e]);
             } else if (line < P) {
                 const float* ub = a.u_t + ((long long)line * P + kb);
                 // output sign (-1)^(r + c): k_off is even, so it is one value per thread and line
@@ -413,7 +425,7 @@ __global__ void __launch_bounds__(THREADS, MINB) screen_detect_radix(const __gri
 #pragma unroll
                 for (int e = 0; e < E; ++e) {
                     if (need & (1u << e)) {
-                        const float uu = __ldg(ub + F::k_off(e));
+                        const float uu = FASTB_DBG(a, 8) ? 1.f : __ldg(ub + F::k_off(e));
                         if (SH) {
                             const float2 sp = sh_phase(sh_tab + (kb + F::k_off(e)) * kShTab, ex);
                             accumulate(make_float2(fmaf(sgn, v[e].x, sp.x), fmaf(sgn, v[e].y, sp.y)), uu, uu, acc);
@@ -826,6 +838,27 @@ int launch_radix_e(const RunArgs& args, bool rng, int max_grid, cudaStream_t st)
             if (v == 646) { kern = screen_detect_radix<F, true, false, 64, 6>; threads = 64; }
         }
     }
+    // tuning builds only: FASTB_SHAPE=<threads><min blocks> for the 16-element flavour
+    if constexpr (E == 16) {
+        if (rng && !sh) {
+            const char* e = getenv("FASTB_SHAPE");
+            const int v = e ? atoi(e) : 0;
+            if constexpr (LOG2N <= 9) {
+                if (v == 648) { kern = screen_detect_radix<F, true, false, 64, 8>; threads = 64; }
+                if (v == 6410) { kern = screen_detect_radix<F, true, false, 64, 10>; threads = 64; }
+                if (v == 6412) { kern = screen_detect_radix<F, true, false, 64, 12>; threads = 64; }
+            }
+            if constexpr (LOG2N <= 10) {
+                if (v == 1284) { kern = screen_detect_radix<F, true, false, 128, 4>; threads = 128; }
+                if (v == 1285) { kern = screen_detect_radix<F, true, false, 128, 5>; threads = 128; }
+                if (v == 1286) { kern = screen_detect_radix<F, true, false, 128, 6>; threads = 128; }
+                if (v == 1288) { kern = screen_detect_radix<F, true, false, 128, 8>; threads = 128; }
+            }
+            if (v == 2562) { kern = screen_detect_radix<F, true, false, 256, 2>; threads = 256; }
+            if (v == 2563) { kern = screen_detect_radix<F, true, false, 256, 3>; threads = 256; }
+            if (v == 2564) { kern = screen_detect_radix<F, true, false, 256, 4>; threads = 256; }
+        }
+    }
     // tuning builds only: FASTB_TMA=1|2|3 routes weights+scratch / scratch only / weights only
     // through per-warp TMA staging (cp.async.bulk + mbarrier) on the bench path
     if constexpr (E == 16) {
@@ -958,6 +991,9 @@ extern "C" int fastb_screen_detect(const FastbRunParams* p, const float* d_weigh
     a.scratch = (float2*)((char*)d_workspace + ut);
     a.rows_per_block = direct_rows(p->n);
     a.phs = nullptr;
+#ifdef FASTB_TUNE
+    a.dbg = getenv("FASTB_DBG") ? atoi(getenv("FASTB_DBG")) : 0;
+#endif
     a.sh_weight = nullptr;
     a.sh_noise = a.sh_ex = a.sh_ey = a.sh_mean = nullptr;
     if (sh) {
