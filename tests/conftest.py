@@ -16,6 +16,11 @@ def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')
 
 
+def load_golden_arrays(name):
+    """A golden npz without a config (tests/golden/comms.npz)."""
+    return dict(np.load(os.path.join(GOLDEN, name + '.npz'), allow_pickle=False))
+
+
 def load_golden(name):
     """Golden npz written by oracle/make_golden.py + the params dict that produced it."""
     from oracle import configs
