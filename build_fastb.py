@@ -23,6 +23,7 @@ SOURCES = {
     'psd_build.cu': ['-fmad=false'],
     'screen_detect.cu': ['-Xptxas', '-v'] + (['-DFASTB_TUNE'] if os.environ.get('FASTB_TUNE') else []),
     'stats.cu': [],
+    'link_metrics.cu': ['-fmad=false'],
     'temporal.cu': [],
 }
 

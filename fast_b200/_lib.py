@@ -70,7 +70,15 @@ class TemporalParams(C.Structure):
                 ('n_steps', C.c_int64), ('u_sum', C.c_double)]
 
 
+class ModParams(C.Structure):
+    _fields_ = [('n', C.c_int64), ('first', C.c_int64), ('symbols_per_iter', C.c_int32),
+                ('n_symbols', C.c_int32), ('scheme', C.c_int32), ('has_awgn', C.c_int32),
+                ('es', C.c_double), ('snr_scale', C.c_double), ('seed', C.c_uint64)]
+
+
 LAYER_PAIR_BASE = 1 << 62
+CURVE_BER_OOK, CURVE_SEP_QAM = 0, 1
+MOD_OOK, MOD_BPSK, MOD_NEAREST = 0, 1, 2
 
 # every symbol include/fastb.h declares (tests/test_abi.py checks the list against the header)
 _SIGS = {
@@ -93,6 +101,19 @@ _SIGS = {
     'fastb_temporal_detect': (C.c_int, [C.POINTER(TemporalParams)] + [C.c_void_p] * 8 + [C.c_void_p]),
     'fastb_stats': (C.c_int, [C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_int32, C.c_void_p,
                               C.c_void_p, C.c_void_p, C.c_void_p]),
+    'fastb_error_curve': (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
+                                    C.c_void_p, C.c_void_p]),
+    'fastb_fade_stats': (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    'fastb_modulator_mc': (C.c_int, [C.POINTER(ModParams)] + [C.c_void_p] * 8),
+    'fastb_amplitudes': (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'fastb_iq_histogram': (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                     C.c_int32, C.c_void_p, C.c_void_p]),
+    'fastb_iq_convolve_workspace_bytes': (C.c_int64, [C.c_int32, C.c_int32]),
+    'fastb_iq_convolve': (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
+                                    C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_int64, C.c_void_p]),
+    'fastb_iq_information': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
+                                       C.c_void_p]),
     'fastb_version': (C.c_int, []),
     'fastb_last_error': (C.c_char_p, []),
     'fastb_device_count': (C.c_int, []),
@@ -250,3 +271,69 @@ def temporal_detect(tp: TemporalParams, screens, xi, xf, yi, yf, U, chi, out):
     _check(lib.fastb_temporal_detect(C.byref(tp), _ptr(screens, f32), _ptr(xi, i32), _ptr(xf, f32),
                                      _ptr(yi, i32), _ptr(yf, f32), _ptr(U, f32), _ptr(chi, f32),
                                      _ptr(out, f32), _stream()), 'fastb_temporal_detect')
+
+
+# ---- K5: link metrics (fast/comms.py consumers) --------------------------------------------
+def error_curve(samples, kind, qam_order, snr_db):
+    """-> float64 tensor [k + 1]: curve and the sample mean."""
+    out = torch.empty(snr_db.numel() + 1, dtype=torch.float64, device=samples.device)
+    _check(lib.fastb_error_curve(_ptr(samples, torch.float32), samples.numel(), int(kind), int(qam_order),
+                                 _ptr(snr_db, torch.float64), snr_db.numel(), _ptr(out), _stream()),
+           'fastb_error_curve')
+    return out
+
+
+def fade_stats(series, thresholds):
+    """-> int64 tensor [k, 4]: below, complete fades, samples inside them, last index not below."""
+    out = torch.empty((thresholds.numel(), 4), dtype=torch.int64, device=series.device)
+    _check(lib.fastb_fade_stats(_ptr(series, torch.float32), series.numel(), _ptr(thresholds, torch.float64),
+                                thresholds.numel(), _ptr(out), _stream()), 'fastb_fade_stats')
+    return out
+
+
+def modulator_mc(mp: ModParams, power, constellation, sums, symbols=None, recv=None, recv_symbols=None,
+                 tx_symbols=None):
+    _check(lib.fastb_modulator_mc(C.byref(mp), _ptr(power, torch.float32), _ptr(constellation, torch.float32),
+                                  _ptr(sums, torch.float64), _ptr(symbols, torch.uint8),
+                                  _ptr(recv, torch.float32), _ptr(recv_symbols, torch.uint8),
+                                  _ptr(tx_symbols, torch.uint8), _stream()), 'fastb_modulator_mc')
+
+
+def amplitudes(samples, is_complex):
+    """-> (float64 |z| [n], float64 [2] = sum |z|, sum |z|^2)."""
+    n = samples.numel() // (2 if is_complex else 1)
+    amp = torch.empty(n, dtype=torch.float64, device=samples.device)
+    sums = torch.empty(2, dtype=torch.float64, device=samples.device)
+    _check(lib.fastb_amplitudes(_ptr(samples, torch.float32), int(bool(is_complex)), n, _ptr(amp), _ptr(sums),
+                                _stream()), 'fastb_amplitudes')
+    return amp, sums
+
+
+def iq_histogram(amp, points, edges_x, edges_y, npxls):
+    m = points.numel() // 2
+    counts = torch.empty((m, npxls, npxls), dtype=torch.int32, device=amp.device)
+    _check(lib.fastb_iq_histogram(_ptr(amp, torch.float64), amp.numel(), _ptr(points, torch.float64), m,
+                                  _ptr(edges_x, torch.float64), _ptr(edges_y, torch.float64), int(npxls),
+                                  _ptr(counts), _stream()), 'fastb_iq_histogram')
+    return counts
+
+
+def iq_convolve(counts, n, taps, shot=False, sigma2=1.0, mean_amp=1.0, edges_x=None, edges_y=None):
+    m, npxls, _ = counts.shape
+    nbytes = lib.fastb_iq_convolve_workspace_bytes(m, npxls)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=counts.device)
+    out = torch.empty((m, npxls, npxls), dtype=torch.float64, device=counts.device)
+    _check(lib.fastb_iq_convolve(_ptr(counts, torch.int32), int(n), m, npxls, _ptr(taps, torch.float64),
+                                 int(bool(shot)), float(sigma2), float(mean_amp), _ptr(edges_x, torch.float64),
+                                 _ptr(edges_y, torch.float64), _ptr(out), _ptr(ws), nbytes, _stream()),
+           'fastb_iq_convolve')
+    return out
+
+
+def iq_information(f, gray, n_bits):
+    """-> float64 [2]: mutual information, generalised mutual information (bits/symbol)."""
+    m, npxls, _ = f.shape
+    out = torch.empty(2, dtype=torch.float64, device=f.device)
+    _check(lib.fastb_iq_information(_ptr(f, torch.float64), m, npxls, _ptr(gray, torch.int32), int(n_bits),
+                                    _ptr(out), _stream()), 'fastb_iq_information')
+    return out

@@ -276,6 +276,99 @@ int fastb_stats(const float* d_r, int64_t n, double db_lo, double db_hi, int32_t
                 double* d_sums, double* d_minmax, unsigned long long* d_hist, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * K5: link metrics on the per-realisation results (consumers of FastResult.power,
+ * fast/comms.py).  All arrays are device pointers; outputs are overwritten (not accumulated)
+ * unless stated.  Arithmetic is float64 on the float32 samples, as the reference computes on
+ * float64 copies of the same values.
+ * ------------------------------------------------------------------------------------- */
+enum { FASTB_CURVE_BER_OOK = 0, FASTB_CURVE_SEP_QAM = 1 };
+
+/* Mean over the samples of a closed-form error probability, one value per SNR point; replaces
+ * ber_ook / sep_qam (fast/comms.py:193-240; ber_qam :243-253 is sep_qam rescaled by the caller):
+ *   s_i = x_i / mean(x)
+ *   BER_OOK : Q(s_i sqrt(10^(snr_db/10)))
+ *   SEP_QAM : 4 (a q - a^2 q^2), q = Q(sqrt(3/(M-1) 10^(snr_db/10) s_i^2)), a = (sqrt M - 1)/sqrt M
+ * d_curve has k + 1 doubles: [0, k) the curve, [k] the sample mean that was used. */
+int fastb_error_curve(const float* d_samples, int64_t n, int32_t kind, int32_t qam_order,
+                      const double* d_snr_db, int32_t k, double* d_curve, void* stream);
+
+/* Fade statistics of a time series for k thresholds; replaces fade_prob / fade_dur
+ * (fast/comms.py:171-191).  d_out[4 j + {0,1,2,3}] = samples below threshold j, complete fades,
+ * samples inside complete fades, index of the last sample not below the threshold (-1 if none).
+ * A complete fade is a maximal below-threshold run that starts at index >= 1 and ends before the
+ * last sample (the reference drops a fade in progress at either end of the window).
+ * probability = out[0]/n; mean duration = dt out[2]/out[1]. */
+int fastb_fade_stats(const float* d_series, int64_t n, const double* d_thresholds, int32_t k,
+                     int64_t* d_out, void* stream);
+
+/* Monte-Carlo modulator; replaces Modulator.run (fast/comms.py:13-146): for realisation i and
+ * symbol slot s < symbols_per_iter draw a symbol, add AWGN of standard deviation
+ *   OOK: Es / snr_i (real)      otherwise: sqrt(Es/2) / snr_i per component,
+ *   snr_i = sqrt(10^(EsN0/10)) x_i / mean(x)          (= snr_scale * x_i)
+ * and decide: OOK re > 0.5; BPSK re < 0 -> symbol 1; otherwise the nearest constellation point
+ * (lowest index wins ties).  Es = mean |c|^2 over the constellation.
+ * RNG (statistical parity; the reference uses numpy's unseeded global generator): Philox4x32-10,
+ * key = seed, counter (i lo, i hi, s, 0x30D0A700) with i = first + local index -> words w0..w3:
+ * symbol = (w0 * n_symbols) >> 32; noise = Box-Muller of (w1 >> 9, w2 >> 9) as in K2.
+ * d_sums[3] += { symbol errors, sum |rx - tx|, sum |tx|^2 } over n * symbols_per_iter draws
+ * (accumulated: the caller zeroes it; sum-reducible over ranks):
+ *   SEP = sums[0] / (n S);   EVM = (sums[1] / (n S)) / sqrt(sums[2] / (n S)).
+ * Optional outputs, [s * n + i] like the reference's (S, n) arrays, any may be NULL:
+ * d_symbols (uint8), d_recv (float2), d_recv_symbols (uint8).
+ * d_tx_symbols (optional, symbols_per_iter uint8): transmit this sequence in every realisation
+ * instead of random symbols (the reference's `data` mode, fast/comms.py:53-56). */
+enum { FASTB_MOD_OOK = 0, FASTB_MOD_BPSK = 1, FASTB_MOD_NEAREST = 2 };
+typedef struct FastbModParams {
+    int64_t n;                 /* realisations on this rank */
+    int64_t first;             /* global index of the first one (RNG counter) */
+    int32_t symbols_per_iter;
+    int32_t n_symbols;         /* <= 1024 */
+    int32_t scheme;            /* FASTB_MOD_* */
+    int32_t has_awgn;          /* 0: EsN0 = None */
+    double es;                 /* mean |c|^2 */
+    double snr_scale;          /* sqrt(10^(EsN0/10)) / mean(x) */
+    uint64_t seed;
+} FastbModParams;
+int fastb_modulator_mc(const FastbModParams* p, const float* d_power, const float* d_constellation /* 2 n_symbols: re, im */,
+                       double* d_sums, uint8_t* d_symbols, float* d_recv /* 2 n S */, uint8_t* d_recv_symbols,
+                       const uint8_t* d_tx_symbols, void* stream);
+
+/* |z_i| of the samples in float64 (is_complex: d_samples holds n (re, im) pairs, else n reals)
+ * and d_sums[2] = { sum |z|, sum |z|^2 } (overwritten); feeds the geometry of the I-Q histograms
+ * (numpy.abs(samples), numpy.mean(numpy.abs(samples)), fast/comms.py:355-356,390). */
+int fastb_amplitudes(const float* d_samples, int32_t is_complex, int64_t n, double* d_amp,
+                     double* d_sums, void* stream);
+
+/* I-Q plane histograms; replaces the binning of convolve_awgn_qam (fast/comms.py:380-393):
+ * for every constellation point c the samples z = c * amp_i are binned on the edges
+ * d_edges_x[c][0..npxls], d_edges_y[c][0..npxls] with numpy.histogram2d's rule (right-open bins,
+ * last edge inclusive, outside values dropped).  d_counts[c][ix][iy] (uint32) is overwritten. */
+int fastb_iq_histogram(const double* d_amp, int64_t n, const double* d_points /* 2 M: re, im */, int32_t m,
+                       const double* d_edges_x, const double* d_edges_y, int32_t npxls,
+                       uint32_t* d_counts, void* stream);
+
+/* AWGN convolution of the histograms; replaces fast/comms.py:395-411.
+ *   shot == 0: out[c] = G h G^T, h = counts / n, G[i][j] = taps[j - i + (npxls+1)/2] (zero outside:
+ *              scipy.ndimage.correlate1d, mode 'constant'), taps has npxls + 1 entries.
+ *   shot != 0: every occupied bin (i, j) spreads as exp(-((i-y)^2 + (j-x)^2) / (sigma2 mult)) h /
+ *              (pi sigma2 mult), mult = mean_amp^2 / (edges_x[c][i]^2 + edges_y[c][j]^2).
+ * d_out: m * npxls * npxls doubles; d_workspace: fastb_iq_convolve_workspace_bytes(m, npxls). */
+int64_t fastb_iq_convolve_workspace_bytes(int32_t m, int32_t npxls);
+int fastb_iq_convolve(const uint32_t* d_counts, int64_t n, int32_t m, int32_t npxls, const double* d_taps,
+                      int32_t shot, double sigma2, double mean_amp, const double* d_edges_x,
+                      const double* d_edges_y, double* d_out, void* d_workspace, int64_t workspace_bytes,
+                      void* stream);
+
+/* Mutual information measures of the convolved histograms f[c][pixel]; replaces the reductions
+ * of mutual_information_qam / generalised_mutual_information_qam (fast/comms.py:262-303), with
+ * x log2 x := 0 for x <= 0 (the reference's masked-array semantics):
+ *   d_out[0] = (1/M) sum_c sum_pix f_c (log2 f_c - log2 fy),           fy = mean_c f_c
+ *   d_out[1] = sum_{bit b < n_bits} 1/2 sum_pix sum_{v in {0,1}} fb_v (log2 fb_v - log2 fy),
+ *              fb_v = mean of f_c over the symbols whose bit b (from the MSB) of d_gray[c] is v. */
+int fastb_iq_information(const double* d_f, int32_t m, int32_t npxls, const uint32_t* d_gray, int32_t n_bits,
+                         double* d_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * library
  * ------------------------------------------------------------------------------------- */
 int fastb_version(void);
