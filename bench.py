@@ -220,6 +220,65 @@ def cufft_comparator(sim, n_real, steps, batch_pairs=256):
 
 
 # ------------------------------------------------------------------------- GPU
+# ------------------------------------------------------------------------- K5 link metrics
+def k5_link_metrics(with_cpu):
+    """Secondary figures for the consumers of the per-realisation output:
+    device time of each K5 entry point on synthetic samples (CUDA events, best of 5 after a
+    warm-up) and the CPU oracle (numpy, 1 core) on a bounded sample of the same work."""
+    import numpy as np
+    import torch
+    from fast_b200 import _lib, comms
+    rng = np.random.default_rng(1)
+    n = 4_000_000
+    host = np.exp(0.35 * rng.standard_normal(n)).astype(np.float32)
+    x = torch.from_numpy(host).cuda()
+    snr = torch.linspace(0, 30, 32, dtype=torch.float64).cuda()
+    thr = torch.tensor([0.1, 0.2, 0.3, 0.5, 0.7, 1.0, 1.5, 2.0], dtype=torch.float64).cuda()
+
+    def timed(fn, reps=5):
+        fn()
+        torch.cuda.synchronize()
+        best = 1e30
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return best
+
+    out = {}
+    ms = timed(lambda: _lib.error_curve(x, _lib.CURVE_SEP_QAM, 16, snr))
+    out["error_curve"] = {"ms": ms, "samples": n, "snr_points": 32, "evaluations_per_s": n * 32 / (ms * 1e-3)}
+    ms = timed(lambda: _lib.fade_stats(x, thr))
+    out["fade_stats"] = {"ms": ms, "samples": n, "thresholds": 8, "GB_per_s": n * 4 * 8 / (ms * 1e6)}
+    mod = comms.Modulator(x[:100_000], '16-QAM', EsN0=12.0, symbols_per_iter=1000, seed=1)
+    ms = timed(lambda: mod.run(), reps=3)
+    out["modulator_16qam"] = {"ms": ms, "symbols": 100_000 * 1000, "symbols_per_s": 1e8 / (ms * 1e-3),
+                              "sep": mod.sep, "note": "fused draw + AWGN + nearest-point decision; includes host glue"}
+    amp = torch.sqrt(x[:1_000_000]).contiguous()
+    ms = timed(lambda: comms._information(amp, 16, 128, 14.0, None, False), reps=3)
+    out["iq_information_16qam_128px"] = {"ms": ms, "samples": 1_000_000,
+                                         "note": "amplitudes + histograms + AWGN convolution + MI/GMI"}
+    if with_cpu:
+        from oracle import comms_oracle as co
+        sub = host[:250_000].astype(np.float64)
+        t0 = time.perf_counter()
+        for s_db in (0.0, 10.0, 20.0, 30.0):
+            co.sep_qam(16, s_db, sub)
+        dt = time.perf_counter() - t0
+        out["error_curve"]["cpu_oracle_evaluations_per_s"] = sub.size * 4 / dt
+        np.random.seed(1)
+        t0 = time.perf_counter()
+        co.modulator(host[:2000].astype(np.float64), '16-QAM', 12.0, 100)
+        out["modulator_16qam"]["cpu_oracle_symbols_per_s"] = 2000 * 100 / (time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        co.mutual_information_qam(np.sqrt(sub[:100_000]), 16, 128, 14.0)
+        out["iq_information_16qam_128px"]["cpu_oracle_ms_100k_samples_mi_only"] = 1e3 * (time.perf_counter() - t0)
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as td
@@ -352,6 +411,7 @@ def run_ours(args):
         comparator = None
         if world == 1 and not args.no_comparator and not coherent:
             comparator = cufft_comparator(sim, n_real, max(2, args.steps // 4))
+        k5 = k5_link_metrics(not args.no_cpu) if world == 1 and not args.no_comparator else None
         cpu = None
         if world == 1 and not args.no_cpu:
             n_cpu = {'c2': 2000, 'c4': 500, 'c5': 120}[args.workload]
@@ -377,6 +437,7 @@ def run_ours(args):
                 "comparator": comparator,
                 "k1_psd_build": {"compute_powerspec_ms": min(k1_ms), "note": "K1 + Simpson + pupil filter incl. host glue; "
                                  "CPU counterpart is cpu_baseline.psd_build_s"},
+                "k5_link_metrics": k5,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": int(launches),
                 "clocks": sampler.summary(),
