@@ -42,7 +42,8 @@ struct RunArgs {
     float* phs;               // direct kernel only: write the cropped screens instead of detecting
 #ifdef FASTB_TUNE
     int dbg;                  // timing experiments (results wrong): 1 no scratch stores, 2 no weight
-                              // loads, 4 no scratch loads, 8 no detector loads, 16 no noise
+                              // loads, 4 no scratch loads, 8 no detector loads, 16 no noise, 32 no
+                              // MUFU in Box-Muller, 64 cheap hash instead of Philox, 128 no detector sincos
 #endif
 };
 #ifdef FASTB_TUNE
@@ -379,11 +380,27 @@ __global__ void __launch_bounds__(THREADS, MINB) screen_detect_radix(const __gri
 #pragma unroll
                     for (int h = 0; h < E / 16; ++h) {
                         uint32_t mr[16], ma[16];
-                        noise_block_fields((uint32_t)(line * (N / 16) + u + S1 * h), g, k0, k1, mr, ma);
+                        if (FASTB_DBG(a, 64)) {                 // timing only: a cheap hash instead of Philox
+                            uint32_t x = (uint32_t)(line * (N / 16) + u + S1 * h) * 0x9E3779B9u + (uint32_t)g;
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                x = x * 1664525u + 1013904223u;
+                                mr[j] = x >> 9;
+                                ma[j] = (x * 0x85EBCA6Bu) >> 9;
+                            }
+                        } else {
+                            noise_block_fields((uint32_t)(line * (N / 16) + u + S1 * h), g, k0, k1, mr, ma);
+                        }
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             const int m = (E / 16) * j + h;
-                            v[m] = weighted_normal_m(mr[j], ma[j], w[m]);
+                            if (FASTB_DBG(a, 32)) {             // timing only: no MUFU in Box-Muller
+                                const float fr = __uint_as_float(0x3f800000u | mr[j]) - 1.5f;
+                                const float fa = __uint_as_float(0x3f800000u | ma[j]) - 1.5f;
+                                v[m] = make_float2(fr * w[m], fa * w[m]);
+                            } else {
+                                v[m] = weighted_normal_m(mr[j], ma[j], w[m]);
+                            }
                         }
                     }
                 } else {
