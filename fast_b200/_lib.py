@@ -70,6 +70,12 @@ class TemporalParams(C.Structure):
                 ('n_steps', C.c_int64), ('u_sum', C.c_double)]
 
 
+class ZernikeParams(C.Structure):
+    _fields_ = [('n', C.c_int32), ('noll_first', C.c_int32), ('noll_last', C.c_int32), ('gtilt', C.c_int32),
+                ('clip_box', C.c_int32), ('reserved', C.c_int32), ('df', C.c_double), ('diameter', C.c_double),
+                ('d_wfs', C.c_double), ('modal_mult', C.c_double)]
+
+
 class ModParams(C.Structure):
     _fields_ = [('n', C.c_int64), ('first', C.c_int64), ('symbols_per_iter', C.c_int32),
                 ('n_symbols', C.c_int32), ('scheme', C.c_int32), ('has_awgn', C.c_int32),
@@ -83,6 +89,7 @@ MOD_OOK, MOD_BPSK, MOD_NEAREST = 0, 1, 2
 # every symbol include/fastb.h declares (tests/test_abi.py checks the list against the header)
 _SIGS = {
     'fastb_psd_build': (C.c_int, [C.POINTER(PsdParams), C.POINTER(PsdInputs), C.POINTER(PsdOutputs), C.c_void_p]),
+    'fastb_zernike_filter': (C.c_int, [C.POINTER(ZernikeParams), C.c_void_p, C.c_void_p]),
     'fastb_make_weight': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_void_p, C.c_void_p]),
     'fastb_simpson2d': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     'fastb_pupil_filter': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
@@ -176,6 +183,17 @@ def psd_build(params: PsdParams, outputs: dict, lf_mask=None, zfilter=None, pupi
         want = torch.float32 if name.startswith('weight') else f64
         setattr(outs, 'd_' + name, _ptr(t, want))
     _check(lib.fastb_psd_build(C.byref(params), C.byref(ins), C.byref(outs), _stream()), 'fastb_psd_build')
+
+
+def zernike_filter(n, df, device, noll_first=1, noll_last=0, diameter=0.0, d_wfs=0.0, modal_mult=1.0,
+                   gtilt=False, clip_box=False):
+    """Zernike squared filter / modal corrected-region mask on the n x n grid -> float64 [n, n]."""
+    zp = ZernikeParams(n=int(n), noll_first=int(noll_first), noll_last=int(noll_last), gtilt=int(bool(gtilt)),
+                       clip_box=int(bool(clip_box)), df=float(df), diameter=float(diameter), d_wfs=float(d_wfs),
+                       modal_mult=float(modal_mult))
+    out = torch.empty((n, n), dtype=torch.float64, device=device)
+    _check(lib.fastb_zernike_filter(C.byref(zp), _ptr(out), _stream()), 'fastb_zernike_filter')
+    return out
 
 
 def make_weight(W, df, out=None):

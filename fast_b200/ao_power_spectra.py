@@ -1,9 +1,9 @@
-"""Host-side pieces of the reference's `fast.ao_power_spectra` that are NOT on the device:
-the Bessel-function based masks for modal / tip-tilt / LGS correction
-(fast/ao_power_spectra.py:10-141).  They are evaluated once per configuration with
-scipy.special and handed to fastb_psd_build as per-pixel arrays.  The per-pixel PSD terms
-themselves (G_AO_PAOLA, Jol_alias_openloop, Jol_noise_openloop, logamp_powerspec) are computed
-by the CUDA library."""
+"""Host-side counterparts of the reference's `fast.ao_power_spectra` mask helpers
+(fast/ao_power_spectra.py:10-141), kept for API compatibility (`mask_lf`, `zernike_ft`,
+`zernike_squared_filter` are public names of the reference) and for the TEMPORAL frequency
+grids.  `Fast` itself builds the modal / tip-tilt / LGS masks on the device
+(`fastb_zernike_filter`); the per-pixel PSD terms (G_AO_PAOLA, Jol_alias_openloop,
+Jol_noise_openloop, logamp_powerspec) are computed by the CUDA library."""
 import warnings
 
 import numpy

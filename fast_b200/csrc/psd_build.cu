@@ -272,10 +272,78 @@ __global__ void pf_centre_kernel(double* __restrict__ pf, int n) {
     pf[(size_t)(n / 2) * n + n / 2] = 1.0;
 }
 
+
+// ---- modal masks: Fourier-space Zernike filters (fast/ao_power_spectra.py:10-141) -----------
+// |Z_j(f)|^2 of Noll (1976): radial order n, azimuthal order m of Noll index j,
+//   m == 0 : (n + 1) (2 J_{n+1}(x) / x)^2                     x = |f| D / 2
+//   m != 0 : 2 (n + 1) (2 J_{n+1}(x) / x)^2 {cos, sin}^2(m phi)   (cos for even j), phi = atan2(fy, fx)
+// summed over j = noll_first .. noll_last; DC pixel := 1 if the sum starts at j = 1, else 0.
+__global__ void __launch_bounds__(128) zernike_filter_kernel(const __grid_constant__ FastbZernikeParams p,
+                                                             double* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+    if (c >= p.n) return;
+    const int half = p.n / 2;
+    const double fx = (double)(c - half) * p.df, fy = (double)(r - half) * p.df;
+    const double fabs_ = sqrt(fx * fx + fy * fy);
+    double val;
+    if (p.noll_last < p.noll_first) {
+        // modal DM without a Zernike limit: a disc of radius modal_mult * pi / d
+        val = (fabs_ <= M_PI / p.d_wfs * p.modal_mult) ? 1.0 : 0.0;
+    } else {
+        const double x = fabs_ * p.diameter / 2.0;
+        const double phi = atan2(fy, fx);
+        val = 0.0;
+        int n_prev = -1;
+        double radial2 = 0.0;
+        for (int j = p.noll_first; j <= p.noll_last; ++j) {
+            // aotools zernIndex: Noll j -> (n, |m|)
+            const int n = (int)((-1.0 + sqrt((double)(8 * (j - 1) + 1))) / 2.0);
+            const int pj = j - n * (n + 1) / 2;
+            const int k = n % 2;
+            const int m = ((pj + k) / 2) * 2 - k;
+            if (n != n_prev) {
+                const double radial = 2.0 * jn(n + 1, x) / x;
+                radial2 = radial * radial;
+                n_prev = n;
+            }
+            if (m == 0) {
+                val += (double)(n + 1) * radial2;
+            } else {
+                const double az = (j % 2 == 0) ? cos((double)m * phi) : sin((double)m * phi);
+                val += 2.0 * (double)(n + 1) * radial2 * (az * az);
+            }
+        }
+        if (r == half && c == half) val = (p.noll_first == 1) ? 1.0 : 0.0;
+        if (p.gtilt) {
+            const double j1 = jn(1, x);
+            val += j1 * j1;
+        }
+    }
+    if (p.clip_box) {
+        // mask_lf: WFS box |fx|, |fy| <= pi/d times the DM term clipped to <= 1 (NaN -> 1)
+        const double fmax = M_PI / p.d_wfs;
+        const double dm = (val < 1.0) ? val : 1.0;
+        val = (fabs(fx) <= fmax && fabs(fy) <= fmax) ? dm : 0.0;
+    }
+    out[(size_t)r * p.n + c] = val;
+}
+
 }  // namespace
 }  // namespace fastb
 
 using namespace fastb;
+
+extern "C" int fastb_zernike_filter(const FastbZernikeParams* p, double* d_out, void* stream) {
+    FASTB_REQUIRE(p && d_out, "fastb_zernike_filter: NULL pointer");
+    FASTB_REQUIRE(p->n >= 2, "fastb_zernike_filter: n=%d must be >= 2", p->n);
+    FASTB_REQUIRE(p->noll_first >= 1 && p->noll_last <= 100000, "fastb_zernike_filter: Noll range out of bounds");
+    FASTB_REQUIRE(p->noll_last < p->noll_first || p->diameter > 0.0, "fastb_zernike_filter: diameter must be > 0");
+    FASTB_REQUIRE(!(p->clip_box || p->noll_last < p->noll_first) || p->d_wfs > 0.0,
+                  "fastb_zernike_filter: d_wfs must be > 0 for the box / disc");
+    dim3 block(128), grid((p->n + 127) / 128, p->n);
+    zernike_filter_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(*p, d_out);
+    return check_launch("zernike_filter_kernel");
+}
 
 extern "C" int fastb_psd_build(const FastbPsdParams* p, const FastbPsdInputs* in,
                                const FastbPsdOutputs* out, void* stream) {

@@ -286,14 +286,29 @@ class Fast():
         if self.ao_mode == 'TT':
             self.Zmax, self.modal, self.modal_mult = 3, True, 1   # tip/tilt = modal, Noll 1..3
 
+    def _modal_mask_device(self, n, df):
+        """mask_lf(modal=True) on the n x n grid of spacing df (fast/ao_power_spectra.py:119-141),
+        evaluated on the device (Bessel-based Zernike filter when ZMAX is given)."""
+        if self.Zmax is None:
+            return _lib.zernike_filter(n, df, self.device, noll_first=1, noll_last=0, d_wfs=self.Dsubap,
+                                       modal_mult=self.modal_mult, clip_box=True)
+        return _lib.zernike_filter(n, df, self.device, noll_first=1, noll_last=self.Zmax,
+                                   diameter=self.D_ground, d_wfs=self.Dsubap, clip_box=True)
+
+    def _lgs_filter_device(self, n, df):
+        """Zernike(1..4) squared filter of the LGSAO branch (fast/ao_power_spectra.py:262-267)."""
+        return _lib.zernike_filter(n, df, self.device, noll_first=1, noll_last=4, diameter=self.D_ground)
+
     @property
     def lf_mask(self):
         """Corrected-region mask as a host array (fast/fast.py:317-319).  Zonal masks are
-        recomputed on the device from fx, fy; modal ones are built here and uploaded."""
+        recomputed inside K1 from fx, fy; modal ones come from fastb_zernike_filter."""
         if 'lf_mask' not in self._host_cache:
-            self._host_cache['lf_mask'] = ao_power_spectra.mask_lf(
-                self.freq.main, self.Dsubap, modal=self.modal, modal_mult=self.modal_mult,
-                Zmax=self.Zmax, D=self.D_ground)
+            if self.modal:
+                m = self._modal_mask_device(self.Npxls, self.freq.main.df).cpu().numpy()
+            else:
+                m = ao_power_spectra.mask_lf(self.freq.main, self.Dsubap)
+            self._host_cache['lf_mask'] = m
         return self._host_cache['lf_mask']
 
     @property
@@ -382,11 +397,9 @@ class Fast():
         d['pupil_filter'] = _lib.pupil_filter(torch.from_numpy(numpy.ascontiguousarray(self._pm_full)).to(dev))
         lf = zf = None
         if self.modal:
-            lf = torch.from_numpy(numpy.ascontiguousarray(self.lf_mask, dtype=float)).to(dev)
+            lf = self._modal_mask_device(N, self.freq.main.df)
         if self.ao_mode == 'LGSAO':
-            fm = self.freq.main
-            z = ao_power_spectra.zernike_squared_filter(fm.fabs, fm.fx, fm.fy, self.D_ground, 4).real
-            zf = torch.from_numpy(numpy.ascontiguousarray(z)).to(dev)
+            zf = self._lgs_filter_device(N, self.freq.main.df)
         # one slab: [aniso_servo, alias, fitting | noise | W | logamp | per-layer (L)]
         slab = torch.zeros((6 + L, N, N), dtype=f64, device=dev)
         d['turb'] = torch.empty((L, N, N), dtype=f64, device=dev)
@@ -432,18 +445,11 @@ class Fast():
         K1 kernel with N = 3 and the level's spacing, plus the plane-wave tables K2 needs."""
         dev, L, f64 = self.device, len(self.h), torch.float64
         sub = self.freq.subharm
-        lf_all = zf_all = None
-        if self.modal:
-            lf_all = numpy.asarray(ao_power_spectra.mask_lf(sub, self.Dsubap, modal=self.modal,
-                                                            modal_mult=self.modal_mult, Zmax=self.Zmax,
-                                                            D=self.D_ground), dtype=float)
-        if self.ao_mode == 'LGSAO':
-            zf_all = ao_power_spectra.zernike_squared_filter(sub.fabs, sub.fx, sub.fy, self.D_ground, 4).real
         W = torch.zeros((3, 3, 3), dtype=f64, device=dev)
         per_layer = torch.zeros((3, L, 3, 3), dtype=f64, device=dev)
         for i in range(3):
-            lf = None if lf_all is None else torch.from_numpy(numpy.ascontiguousarray(lf_all[i])).to(dev)
-            zf = None if zf_all is None else torch.from_numpy(numpy.ascontiguousarray(zf_all[i])).to(dev)
+            lf = self._modal_mask_device(3, sub.df[i]) if self.modal else None
+            zf = self._lgs_filter_device(3, sub.df[i]) if self.ao_mode == 'LGSAO' else None
             _lib.psd_build(self._psd_params(n=3, df=sub.df[i]),
                            {'powerspec': W[i], 'powerspec_per_layer': per_layer[i]}, lf_mask=lf, zfilter=zf)
         self.powerspec_subharm = W.cpu().numpy()

@@ -101,6 +101,21 @@ typedef struct FastbPsdOutputs {
 int fastb_psd_build(const FastbPsdParams* p, const FastbPsdInputs* in,
                     const FastbPsdOutputs* out, void* stream);
 
+/* Modal corrected-region masks and Fourier-space Zernike filters, float64; replaces
+ * ao_power_spectra.zernike_ft / zernike_squared_filter / mask_lf(modal=True)
+ * (fast/ao_power_spectra.py:10-141; used by fast/fast.py:311-319 and G_AO_PAOLA's LGSAO branch
+ * :262-267).  On the n x n frequency grid f = (index - n/2) df:
+ *   noll_first <= noll_last : v = sum_j |Z_j(f)|^2 over the Noll range (disc of `diameter`),
+ *                             DC pixel := 1 if noll_first == 1 else 0;  gtilt: v += J_1(|f| D/2)^2
+ *   noll_last  <  noll_first: v = [ |f| <= modal_mult pi / d_wfs ]       (modal DM, no Zernike limit)
+ *   clip_box                : out = [ |fx|,|fy| <= pi/d_wfs ] * min(v, 1)   (mask_lf) else out = v.
+ * The outputs feed FastbPsdInputs.d_lf_mask / d_zfilter. */
+typedef struct FastbZernikeParams {
+    int32_t n, noll_first, noll_last, gtilt, clip_box, reserved;
+    double df, diameter, d_wfs, modal_mult;
+} FastbZernikeParams;
+int fastb_zernike_filter(const FastbZernikeParams* p, double* d_out, void* stream);
+
 /* d_weight[r*N+c] = (-1)^(r+c) * sqrt(d_W[r*N+c]) * df, for `batch` stacked N x N spectra.
  * Replaces `rand *= numpy.sqrt(self.powerspec)` + `rand * df` (fast/fast.py:594,
  * fast/funcs.py:218) for callers that bring their own PSD. */
