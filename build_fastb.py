@@ -21,7 +21,7 @@ COMMON = ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC', '--expt-relax
 SOURCES = {
     'api.cu': [],
     'psd_build.cu': ['-fmad=false'],
-    'screen_detect.cu': ['-Xptxas', '-v'] + (['-DFASTB_TUNE'] if os.environ.get('FASTB_TUNE') else []),
+    'screen_detect.cu': ['-Xptxas', '-v'] + (['-DFASTB_TUNE'] if os.environ.get('FASTB_TUNE') else []) + (['-DFASTB_TUNE_DBG'] if os.environ.get('FASTB_TUNE_DBG') else []),
     'stats.cu': [],
     'link_metrics.cu': ['-fmad=false'],
     'temporal.cu': [],

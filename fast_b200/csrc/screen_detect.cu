@@ -33,6 +33,7 @@ struct RunArgs {
     float* out_b;
     float2* scratch;          // gridDim.x slots of n*n_pup float2
     int rows_per_block;       // direct kernel only
+    int stage_shift;          // radix kernel: 1 = stage two rows per line slot before storing, 0 = store directly
     // sub-harmonics (NULL weight = off)
     const float* sh_weight;   // 27
     const float2* sh_noise;   // n_pairs*27 or NULL
@@ -40,13 +41,13 @@ struct RunArgs {
     const float2* sh_ey;      // 3*n_pup
     const float2* sh_mean;    // 27
     float* phs;               // direct kernel only: write the cropped screens instead of detecting
-#ifdef FASTB_TUNE
+#ifdef FASTB_TUNE_DBG
     int dbg;                  // timing experiments (results wrong): 1 no scratch stores, 2 no weight
                               // loads, 4 no scratch loads, 8 no detector loads, 16 no noise, 32 no
                               // MUFU in Box-Muller, 64 cheap hash instead of Philox, 128 no detector sincos
 #endif
 };
-#ifdef FASTB_TUNE
+#ifdef FASTB_TUNE_DBG
 #define FASTB_DBG(a, bit) ((a).dbg & (bit))
 #else
 #define FASTB_DBG(a, bit) 0
@@ -280,7 +281,10 @@ __global__ void __launch_bounds__(THREADS, MINB) screen_detect_radix(const __gri
     Tw* twa = reinterpret_cast<Tw*>(smem_raw);
     Tw* twb = twa + F::kTwA;
     float2* bufs = reinterpret_cast<float2*>(twb + F::kTwB);
-    unsigned char* stage_all = reinterpret_cast<unsigned char*>(bufs + LPB * F::kBuf);
+    // pass-1 output staging: per line slot R = 2^stage_shift (1 or 2) planes of n_pup kept outputs
+    const int rs = kTma ? 0 : a.stage_shift, R = 1 << rs;
+    float2* tiles = bufs + LPB * F::kBuf;
+    unsigned char* stage_all = reinterpret_cast<unsigned char*>(tiles + (rs ? LPB * R * a.n_pup : 0));
     uint64_t* bars = reinterpret_cast<uint64_t*>(stage_all + (kTma ? kWarps * kStageBytes : 0));
     float* red = reinterpret_cast<float*>(bars + (kTma ? kWarps : 0));
     float2* sh_amp = reinterpret_cast<float2*>(red + 4 * kWarps);     // SH only
@@ -291,6 +295,7 @@ __global__ void __launch_bounds__(THREADS, MINB) screen_detect_radix(const __gri
     const int warp = tid >> 5, lane = tid & 31;
     float2* buf = bufs + ln * F::kBuf;
     const int P = a.n_pup, lo = a.lo;
+    float2* tile = tiles + ln * R * P;
     unsigned char* stage = stage_all + warp * kStageBytes;
     uint64_t* bar = bars + warp;
     uint32_t parity = 0;
@@ -347,7 +352,11 @@ __global__ void __launch_bounds__(THREADS, MINB) screen_detect_radix(const __gri
                 __syncthreads();                      // every row of T is stored before a column is read
                 if (kTma) prefetch(n1);
             }
-            const int line = (rows ? it : it - n1) * LPB + ln;      // r' (pass 1) or c (pass 2)
+            // pass 1: a line slot takes R (1 or 2) consecutive rows in R consecutive iterations, so
+            // that its kept outputs leave as 16-byte stores of two adjacent rows per column
+            const int sub = it & (R - 1);
+            const int line = rows ? (((it >> rs) * LPB + ln) << rs) + sub       // r'
+                                  : (it - n1) * LPB + ln;                        // c
             // last column iteration: warps whose lines all lie beyond the crop have nothing to do
             // (line barriers involve only the threads of that line)
             if (!rows && line - (ln % kLinesPerWarp) >= P) continue;
@@ -425,11 +434,28 @@ __global__ void __launch_bounds__(THREADS, MINB) screen_detect_radix(const __gri
 
             F::run(u, v, twa, twb, buf, sync);
 
-            if (rows) {
+            if (rows && rs == 0) {
                 float2* tb = T + ((long long)kb * N + line);  // &T[(k - lo) * N + r'] at k_off = 0
 #pragma unroll
                 for (int e = 0; e < E; ++e)
                     if ((need & (1u << e)) && !FASTB_DBG(a, 1)) __stcg(tb + (long long)F::k_off(e) * N, v[e]);
+            } else if (rows) {
+                float2* tl = tile + (sub * P + kb);           // &tile[sub][k - lo] at k_off = 0
+#pragma unroll
+                for (int e = 0; e < E; ++e)
+                    if (need & (1u << e)) tl[F::k_off(e)] = v[e];
+                if (sub == R - 1) {
+                    // flush the slot: column c gets rows line-1, line as one 16-byte store.  The
+                    // tile is next written after the line barriers of the following iteration's
+                    // FFT, so no barrier is needed after the reads.
+                    sync();
+                    float2* tr = T + (line - (R - 1));
+#pragma unroll 2
+                    for (int c = u; c < P; c += S1) {
+                        const float2 x0 = tile[c], x1 = tile[P + c];
+                        __stcg(reinterpret_cast<float4*>(tr + (long long)c * N), make_float4(x0.x, x0.y, x1.x, x1.y));
+                    }
+                }
             } else if (line < P) {
                 const float* ub = a.u_t + ((long long)line * P + kb);
                 // output sign (-1)^(r + c): k_off is even, so it is one value per thread and line
@@ -783,10 +809,11 @@ size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 size_t sh_smem_bytes(bool sh, int n_pup) { return sh ? sizeof(float2) * (28 + (size_t)kShTab * n_pup) : 0; }
 
 template <class F>
-size_t radix_smem_bytes(bool sh, int n_pup, int threads, bool use_tma) {
+size_t radix_smem_bytes(bool sh, int n_pup, int threads, bool use_tma, int stage_shift = 0) {
     const int LPB = threads / F::S1;
     const size_t tma = (F::S1 <= 32 && use_tma) ? (size_t)(threads / 32) * (32 * F::E * 8 + sizeof(uint64_t)) : 0;
-    return sizeof(typename F::Tw) * ((size_t)F::kTwA + F::kTwB) + sizeof(float2) * (size_t)LPB * F::kBuf + tma +
+    const size_t tile = stage_shift ? sizeof(float2) * (size_t)LPB * ((size_t)n_pup << stage_shift) : 0;
+    return sizeof(typename F::Tw) * ((size_t)F::kTwA + F::kTwB) + sizeof(float2) * (size_t)LPB * F::kBuf + tma + tile +
            sizeof(float) * 4 * (threads / 32) + sh_smem_bytes(sh, n_pup);
 }
 
@@ -888,7 +915,31 @@ int launch_radix_e(const RunArgs& args, bool rng, int max_grid, cudaStream_t st)
         }
     }
 #endif
-    return launch_kernel(kern, args, threads, radix_smem_bytes<F>(sh, args.n_pup, threads, use_tma), max_grid, st);
+    // N <= 512: stage two rows per line slot in shared memory and store them as one 16-byte word
+    // per column (a scattered 8-byte store costs the L1 data pipe one wavefront per lane: 49 % of
+    // all wavefronts at N = 256).  Same-box A/B: +1 % at N = 256, +4 % at N = 512, -2 % at N = 1024.
+    // Skipped when the extra shared memory would cost a resident CTA.
+    RunArgs a2 = args;
+    a2.stage_shift = 0;
+    size_t smem = radix_smem_bytes<F>(sh, args.n_pup, threads, use_tma);
+    int want = LOG2N <= 9 ? 1 : 0;
+#ifdef FASTB_TUNE
+    if (const char* e = getenv("FASTB_STAGE")) want = atoi(e) ? 1 : 0;
+#endif
+    const size_t smem2 = radix_smem_bytes<F>(sh, args.n_pup, threads, false, 1);
+    if (!use_tma && want && (F::N / (threads / F::S1)) % 2 == 0 && smem2 <= 227 * 1024) {
+        int occ0 = 0, occ = 0;
+        FASTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        FASTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                        cudaSharedmemCarveoutMaxShared));
+        FASTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ0, kern, threads, smem));
+        FASTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem2));
+        if (occ >= occ0 && occ >= 1) {
+            a2.stage_shift = 1;
+            smem = smem2;
+        }
+    }
+    return launch_kernel(kern, a2, threads, smem, max_grid, st);
 }
 
 // line-pair kernel: N <= 256: 128 threads x 5 CTAs/SM (96 registers); above: 256 x 2 (128 registers)
@@ -1007,8 +1058,9 @@ extern "C" int fastb_screen_detect(const FastbRunParams* p, const float* d_weigh
     a.out_b = d_out_b;
     a.scratch = (float2*)((char*)d_workspace + ut);
     a.rows_per_block = direct_rows(p->n);
+    a.stage_shift = 0;
     a.phs = nullptr;
-#ifdef FASTB_TUNE
+#ifdef FASTB_TUNE_DBG
     a.dbg = getenv("FASTB_DBG") ? atoi(getenv("FASTB_DBG")) : 0;
 #endif
     a.sh_weight = nullptr;
