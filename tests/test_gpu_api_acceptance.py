@@ -115,6 +115,34 @@ def test_sim_coherent(fast, p):                                  # :122-127
     assert sim.I.dtype == complex
 
 
+@pytest.mark.parametrize('scheme', ['OOK', 'BPSK', 'QAM'])
+def test_fast_fsoc(fast, p, scheme):                             # :129-157 (EsN0 left at its default None)
+    sim = fast.comms.FastFSOC(dict(p, MODULATION=scheme))
+    sim.run()
+    assert np.isfinite(sim.I).all()
+    assert hasattr(sim.modulator, "sep")
+    assert np.isfinite(sim.modulator.sep)
+    assert np.isfinite(sim.modulator.evm)
+
+
+def test_fast_fsoc_with_noise(fast, p):
+    sim = fast.comms.FastFSOC(dict(p, MODULATION='16-QAM', EsN0=12.0, TEMPORAL=False, NITER=1000, NCHUNKS=2))
+    sim.run()
+    assert 0.0 < sim.modulator.sep < 1.0 and sim.modulator.evm > 0.0
+
+
+def test_ber_ook(fast, p):                                       # :168-176
+    sim = run_sim(fast, p)
+    assert np.isfinite(fast.comms.ber_ook(10, sim.result.power))
+    assert np.isfinite(fast.comms.ber_ook(10))
+
+
+def test_ber_qam(fast, p):                                       # :178-187
+    sim = run_sim(fast, p)
+    assert np.isfinite(fast.comms.ber_qam(4, 10, samples=sim.result.power))
+    assert np.isfinite(fast.comms.ber_qam(4, 10))
+
+
 def test_consumer_style_postprocessing(fast, p):
     """What fast/comms.py consumes (FastFSOC.run -> Modulator(self.result.power, ...),
     fast/comms.py:159-162): a finite 1-D float array of length NITER and the fade statistics."""
