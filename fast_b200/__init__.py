@@ -8,6 +8,6 @@ Importing the package requires the in-tree CUDA library (python build_fastb.py).
 from . import conf, funcs, turbulence_models, ao_power_spectra, dist   # noqa: F401
 from . import _lib                                                      # noqa: F401
 from .fast import Fast, FastResult, SpatialFrequencies, SpatialFrequencyStruct, load  # noqa: F401
-from . import sweep, configs, comms                                     # noqa: F401
+from . import sweep, configs, comms, complete_orbit_simulation           # noqa: F401
 
 __version__ = "0.1.0"

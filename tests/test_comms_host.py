@@ -65,3 +65,33 @@ def test_symbol_alphabets():
     assert [comms._n_symbols(s) for s in ('OOK', 'BPSK', 'QPSK', 'QAM', '8-PSK', '64-QAM')] == [2, 2, 4, 4, 8, 64]
     with pytest.raises(ValueError, match='not recognised'):
         comms._n_symbols('FSK')
+
+
+# ---- orbit-sweep driver (fast_b200/complete_orbit_simulation.py), host geometry ----------------
+def test_fov_offsets_small_displacements():
+    from fast_b200.complete_orbit_simulation import fov_offsets
+    alt, az, d = np.radians(40.0), np.radians(120.0), np.radians(0.01)
+    dx, dy = fov_offsets(alt, az, alt + d, az)               # higher by 0.01 deg: straight up in the field
+    assert abs(dx) < 1e-9 and dy == pytest.approx(0.01, rel=1e-6)
+    dx, dy = fov_offsets(alt, az, alt - d, az)
+    assert abs(dx) < 1e-9 and dy == pytest.approx(-0.01, rel=1e-6)
+    dx, dy = fov_offsets(alt, az, alt, az + d)               # azimuth step: shrinks with cos(altitude)
+    assert dx == pytest.approx(0.01 * np.cos(alt), rel=1e-4) and abs(dy) < 1e-5
+    dx, dy = fov_offsets(alt, az, alt, az - d)
+    assert dx == pytest.approx(-0.01 * np.cos(alt), rel=1e-4)
+    # separation is preserved: dx^2 + dy^2 = great-circle distance^2
+    a1, z1 = alt + 0.7 * d, az + 1.3 * d
+    dx, dy = fov_offsets(alt, az, a1, z1)
+    sep = np.degrees(np.arccos(np.sin(alt) * np.sin(a1) + np.cos(alt) * np.cos(a1) * np.cos(z1 - az)))
+    assert np.hypot(dx, dy) == pytest.approx(sep, rel=1e-6)
+    # identical directions: 0/0 in the reference too (it then zeroes the NaN)
+    assert all(np.isnan(v) or v == 0 for v in fov_offsets(alt, az, alt, az))
+
+
+def test_orbit_geometry_needs_skyfield_but_fails_clearly():
+    import importlib.util
+    from fast_b200 import complete_orbit_simulation as cos
+    if importlib.util.find_spec('skyfield') is not None:
+        pytest.skip('skyfield is installed')
+    with pytest.raises(ImportError, match='skyfield is required'):
+        cos.get_satellite_obj('stations.tle')

@@ -233,3 +233,31 @@ def test_largest_radix_grid_2048(fast):
         a1, b1 = sim.screen_detect(0, 1, algo=algo)
         np.testing.assert_allclose(a1.cpu().numpy(), a2.cpu().numpy(), rtol=2e-4)
         np.testing.assert_allclose(b1.cpu().numpy(), b2.cpu().numpy(), rtol=2e-4)
+
+
+def test_orbit_sweep_driver_with_injected_geometry(fast):
+    """FAST_sat_orbit (fast/complete_orbit_simulation.py:190-232) with precomputed pass geometry:
+    one Fast per sample with the reference's keys, zero-Cn2 layers dropped, then one batched sweep."""
+    cos = fast.complete_orbit_simulation
+    base = fast.configs.mini()
+    base.update({'NITER': 200, 'NCHUNKS': 2, 'SEED': 2, 'PROP_DIR': 'down'})
+    base['CN2_TURB'] = list(base['CN2_TURB']) + [0.0]
+    base['H_TURB'] = list(base['H_TURB']) + [30000.0]
+    base['WIND_SPD'] = list(base['WIND_SPD']) + [5.0]
+    base['WIND_DIR'] = list(base['WIND_DIR']) + [10.0]
+    alt = np.array([20.0, 45.0, 80.0])
+    geometry = (np.array([[8.0, 1.0], [9.5, 0.5], [10.4, 0.1]]),      # point-ahead angle ["]
+                np.array([[0.3, 0.0], [0.8, 0.1], [2.5, 0.2]]),       # downlink anisoplanatism ["]
+                alt, np.array([10.0, 40.0, 170.0]), 550e3 / np.sin(np.radians(alt)))
+    sims = cos.FAST_sat_orbit(base, {}, None, geometry=geometry)
+    assert sorted(k for k in sims if k != 'altitudes') == ['simulation_0', 'simulation_1', 'simulation_2']
+    np.testing.assert_array_equal(sims['altitudes'], alt)
+    lst = [sims[f'simulation_{i}'] for i in range(3)]
+    assert all(len(s.h) == len(base['H_TURB']) - 1 for s in lst)
+    # lower elevation: longer path through the turbulence -> larger residual phase variance
+    assert lst[0].phs_var > lst[1].phs_var > lst[2].phs_var
+    res = fast.sweep.run_sweep(lst)
+    assert all(np.isfinite(r.power).all() and len(r.power) == 200 for r in res)
+    assert res[0].dB_rel.mean() < res[2].dB_rel.mean()
+    one = cos.FAST_sat(np.array([2.0, 0.0]), dict(fast.configs.mini(), NITER=20, NCHUNKS=2))
+    np.testing.assert_allclose(one.params['ANISO_DL'], np.array([2.0, 0.0]) * one.params['TLOOP'])
