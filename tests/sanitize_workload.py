@@ -1,5 +1,5 @@
 """Small invocations of every kernel family for compute-sanitizer:
-    compute-sanitizer --tool memcheck|racecheck python tests/sanitize_workload.py
+    compute-sanitizer --tool memcheck|racecheck|initcheck|synccheck python tests/sanitize_workload.py
 (profiles/sanitizer_r01.txt holds the round-1 output: 0 errors, 0 hazards).  Not collected by pytest."""
 import os
 import sys
