@@ -395,7 +395,7 @@ struct LineFFT {
 
     // Output index k held in register e of thread u after the last phase, split into a
     // per-thread base and a compile-time offset: k = k_base(u) + k_off(e).  Offsets are even.
-    FASTB_HD static int k_base(int u) {
+    FASTB_HD static constexpr int k_base(int u) {
         if (kThree) return (S2 == 1) ? u : (u / S2) + 16 * (u % S2);
         return u % SF;
     }
@@ -403,13 +403,28 @@ struct LineFFT {
         return kThree ? ((S2 == 1) ? 16 * e : 16 * S2 * (e / S2) + 256 * (e % S2))
                       : SF * (e / SF) + 16 * (e % SF);
     }
-    FASTB_HD static int k_out(int u, int e) { return k_base(u) + k_off(e); }
+    FASTB_HD static constexpr int k_out(int u, int e) { return k_base(u) + k_off(e); }
     FASTB_HD static constexpr bool k_off_all_even() {
         for (int e = 0; e < 16; ++e)
             if (k_off(e) & 1) return false;
         return true;
     }
 };
+
+// Registers that can hold an output inside the centred window [N/2 - half, N/2 + half), over all
+// threads of a line: bit e of the result.  A kernel that only consumes those registers lets the
+// compiler drop the butterflies of the last stage that feed the others (output pruning at compile
+// time; the crop is the same for every line of both passes).
+template <class F>
+FASTB_HD constexpr unsigned keep_mask(int half) {
+    unsigned m = 0;
+    for (int u = 0; u < F::S1; ++u)
+        for (int e = 0; e < F::E; ++e) {
+            const int k = F::k_out(u, e);
+            if (k >= F::N / 2 - half && k < F::N / 2 + half) m |= 1u << e;
+        }
+    return m;
+}
 
 // Line FFT with 32 complex elements per thread for N = 512 (32 x 16) and N = 1024 (32 x 32):
 // S1 = N/32 threads per line, ONE shared-memory exchange per line (tuning flavour, one line).
@@ -481,9 +496,9 @@ struct LineFFT32 {
         sync();
     }
 
-    FASTB_HD static int k_base(int u) { return u; }
+    FASTB_HD static constexpr int k_base(int u) { return u; }
     FASTB_HD static constexpr int k_off(int e) { return S1 == 32 ? 32 * e : 16 * (e / 16) + 32 * (e % 16); }
-    FASTB_HD static int k_out(int u, int e) { return k_base(u) + k_off(e); }
+    FASTB_HD static constexpr int k_out(int u, int e) { return k_base(u) + k_off(e); }
     FASTB_HD static constexpr bool k_off_all_even() {
         for (int e = 0; e < 32; ++e)
             if (k_off(e) & 1) return false;

@@ -264,11 +264,18 @@ constexpr int radix_default_e() { return 16; }
 // a pass.  TMA != 0 (tuning builds, E = 16, lines inside a warp): the warp's contiguous input
 // block of the next iteration is fetched by one cp.async.bulk into a per-warp stage
 // (1: weights and scratch, 2: scratch only, 3: weights only) -- measured slower, off by default.
-template <class F, bool RNG, bool SH, int THREADS, int MINB, int TMA = 0>
+// WIN (compile time) promises that the crop lies inside the centred window of half-width
+// window_half<N>(WIN) (0: no promise): only the registers keep_mask<F>() names can then hold a kept
+// output, and the compiler drops the last-stage butterflies (and shared loads) that feed the others.
+template <int N>
+constexpr int window_half(int win) { return win == 1 ? N / 8 : win == 2 ? 3 * N / 16 : win == 3 ? N / 4 : N; }
+
+template <class F, bool RNG, bool SH, int THREADS, int MINB, int TMA = 0, int WIN = 0>
 __global__ void __launch_bounds__(THREADS, MINB) screen_detect_radix(const __grid_constant__ RunArgs a) {
     constexpr int N = F::N, S1 = F::S1, E = F::E, LPB = THREADS / S1;
     static_assert(THREADS % S1 == 0 && LPB >= 1 && (S1 <= 32 || LPB <= 15), "line/barrier layout");
     static_assert(E == 16 || E == 32, "elements per thread");
+    constexpr unsigned kKeep = WIN == 0 ? 0xffffffffu : keep_mask<F>(window_half<N>(WIN));
     constexpr bool kTma = (S1 <= 32) && TMA != 0 && E == 16;
     constexpr bool kTmaW = kTma && (TMA == 1 || TMA == 3);      // weight rows through the stage
     constexpr bool kTmaT = kTma && (TMA == 1 || TMA == 2);      // scratch columns through the stage
@@ -438,12 +445,13 @@ __global__ void __launch_bounds__(THREADS, MINB) screen_detect_radix(const __gri
                 float2* tb = T + ((long long)kb * N + line);  // &T[(k - lo) * N + r'] at k_off = 0
 #pragma unroll
                 for (int e = 0; e < E; ++e)
-                    if ((need & (1u << e)) && !FASTB_DBG(a, 1)) __stcg(tb + (long long)F::k_off(e) * N, v[e]);
+                    if (((kKeep >> e) & 1u) && (need & (1u << e)) && !FASTB_DBG(a, 1))
+                        __stcg(tb + (long long)F::k_off(e) * N, v[e]);
             } else if (rows) {
                 float2* tl = tile + (sub * P + kb);           // &tile[sub][k - lo] at k_off = 0
 #pragma unroll
                 for (int e = 0; e < E; ++e)
-                    if (need & (1u << e)) tl[F::k_off(e)] = v[e];
+                    if (((kKeep >> e) & 1u) && (need & (1u << e))) tl[F::k_off(e)] = v[e];
                 if (sub == R - 1) {
                     // flush the slot: column c gets rows line-1, line as one 16-byte store.  The
                     // tile is next written after the line barriers of the following iteration's
@@ -467,7 +475,7 @@ __global__ void __launch_bounds__(THREADS, MINB) screen_detect_radix(const __gri
                 }
 #pragma unroll
                 for (int e = 0; e < E; ++e) {
-                    if (need & (1u << e)) {
+                    if (((kKeep >> e) & 1u) && (need & (1u << e))) {
                         const float uu = FASTB_DBG(a, 8) ? 1.f : __ldg(ub + F::k_off(e));
                         if (SH) {
                             const float2 sp = sh_phase(sh_tab + (kb + F::k_off(e)) * kShTab, ex);
@@ -869,6 +877,21 @@ int launch_radix_e(const RunArgs& args, bool rng, int max_grid, cudaStream_t st)
     else kern = rng ? screen_detect_radix<F, true, false, T, M> : screen_detect_radix<F, false, false, T, M>;
     bool use_tma = false;
     int threads = T;
+    // Window-specialised instances (device RNG, no sub-harmonics): the smallest centred window
+    // class that contains the crop.  FAST's pupil crop is centred and 1/6 .. 1/3 of the grid wide.
+    if constexpr (E == 16 && LOG2N >= 8) {
+        if (rng && !sh) {
+            const int lo = args.lo, hi = args.lo + args.n_pup, c = F::N / 2;
+            const int half = (c - lo) > (hi - c) ? (c - lo) : (hi - c);
+            bool spec = lo <= c && hi >= c;
+#ifdef FASTB_TUNE
+            if (const char* e = getenv("FASTB_KEEP")) spec = spec && atoi(e) != 0;
+#endif
+            if (spec && half <= window_half<F::N>(1)) kern = screen_detect_radix<F, true, false, T, M, 0, 1>;
+            else if (spec && half <= window_half<F::N>(2)) kern = screen_detect_radix<F, true, false, T, M, 0, 2>;
+            else if (spec && half <= window_half<F::N>(3)) kern = screen_detect_radix<F, true, false, T, M, 0, 3>;
+        }
+    }
 #ifdef FASTB_TUNE
     // tuning builds only: FASTB_SHAPE=<threads><minblocks> for the 32-element flavour
     if constexpr (E == 32) {

@@ -157,6 +157,34 @@ def test_odd_pupil_widths_on_both_radix_kernels(fast, N, P):
     np.testing.assert_allclose(outs[1], outs[2], rtol=2e-4)
 
 
+@pytest.mark.parametrize('N,lo,P', [
+    (256, 96, 64), (256, 87, 82), (256, 68, 120), (256, 28, 200), (256, 0, 256),     # window classes 1, 2, 3, none, none
+    (256, 90, 60), (256, 100, 100), (256, 10, 60), (256, 200, 56),                  # off-centre crops
+    (512, 192, 128), (512, 175, 162), (512, 130, 250), (512, 6, 500),
+    (1024, 431, 162), (1024, 330, 364), (1024, 257, 510), (2048, 900, 248), (2048, 512, 1024)])
+def test_window_specialised_radix_instances_match_direct(fast, N, lo, P):
+    """The radix kernel picks an instance specialised on the smallest centred window class that
+    contains the crop (compile-time output pruning); every class, the generic fallback and crops
+    that are off-centre must give the direct-DFT kernel's result."""
+    lib = fast._lib
+    dev = torch.device('cuda')
+    gen = torch.Generator(device='cuda').manual_seed(N + lo + P)
+    w = torch.rand(N, N, dtype=torch.float64, device=dev, generator=gen) * 1e-5
+    weight = lib.make_weight(w, 1.5)
+    U = torch.rand(P, P, dtype=torch.float32, device=dev, generator=gen)
+    outs = []
+    for algo in (lib.ALGO_RADIX, lib.ALGO_DIRECT):
+        rp = lib.RunParams()
+        rp.n, rp.n_pup, rp.lo, rp.n_pairs, rp.pairs_per_chunk, rp.seed, rp.algo = N, P, lo, 2, 2, 7, algo
+        rp.u_sum, rp.sigma_chi = float(U.sum()), 0.02
+        ws = torch.empty(lib.screen_detect_workspace_bytes(rp), dtype=torch.uint8, device=dev)
+        a = torch.empty(2, dtype=torch.float32, device=dev)
+        b = torch.empty(2, dtype=torch.float32, device=dev)
+        lib.screen_detect(rp, weight, U, a, b, ws)
+        outs.append(torch.cat([a, b]).cpu().numpy())
+    np.testing.assert_allclose(outs[0], outs[1], rtol=3e-4)
+
+
 def test_results_do_not_depend_on_launch_split(fast):
     """Counter-based RNG on the global pair index: any split of the pair range, hence any
     number of GPUs, gives bit-identical per-realisation values."""
