@@ -887,6 +887,23 @@ int launch_radix_e(const RunArgs& args, bool rng, int max_grid, cudaStream_t st)
 #ifdef FASTB_TUNE
             if (const char* e = getenv("FASTB_KEEP")) spec = spec && atoi(e) != 0;
 #endif
+#ifdef FASTB_TUNE
+            // tuning builds only: FASTB_WSHAPE=<threads><min blocks> for the window-class-2 instance
+            if constexpr (LOG2N == 8 || LOG2N == 9) {
+                const char* e = getenv("FASTB_WSHAPE");
+                const int v = e ? atoi(e) : 0;
+                if (spec && v && half <= window_half<F::N>(2)) {
+                    spec = false;
+                    if (v == 1284) { kern = screen_detect_radix<F, true, false, 128, 4, 0, 2>; threads = 128; }
+                    if (v == 1285) { kern = screen_detect_radix<F, true, false, 128, 5, 0, 2>; threads = 128; }
+                    if (v == 1286) { kern = screen_detect_radix<F, true, false, 128, 6, 0, 2>; threads = 128; }
+                    if (v == 2562) { kern = screen_detect_radix<F, true, false, 256, 2, 0, 2>; threads = 256; }
+                    if (v == 2563) { kern = screen_detect_radix<F, true, false, 256, 3, 0, 2>; threads = 256; }
+                    if (v == 648) { kern = screen_detect_radix<F, true, false, 64, 8, 0, 2>; threads = 64; }
+                    if (v == 6410) { kern = screen_detect_radix<F, true, false, 64, 10, 0, 2>; threads = 64; }
+                }
+            }
+#endif
             if (spec && half <= window_half<F::N>(1)) kern = screen_detect_radix<F, true, false, T, M, 0, 1>;
             else if (spec && half <= window_half<F::N>(2)) kern = screen_detect_radix<F, true, false, T, M, 0, 2>;
             else if (spec && half <= window_half<F::N>(3)) kern = screen_detect_radix<F, true, false, T, M, 0, 3>;
