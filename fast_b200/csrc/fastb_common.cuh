@@ -55,14 +55,23 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
     return make_uint4(c0, c1, c2, c3);
 }
 
+// log2 of a normal (non-denormal) float as the bare MUFU.LG2: __log2f wraps the same instruction in
+// a compare, a predicated 2^24 scaling and a predicated -24 correction for denormal arguments --
+// three more issued instructions per call, and the Box-Muller argument is never below 2^-23.
+__device__ __forceinline__ float lg2_ftz(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // Box-Muller from two 23-bit mantissa fields, scaled by w: radius argument 1 - mr 2^-23 in (0, 1],
 // angle 2 pi ma 2^-23.  The mantissa trick builds 1+u in [1, 2) without an int->float conversion;
 // sin/cos are 2 pi-periodic so 2 pi (1+u) is used directly.
-// 4 MUFU (lg2, sqrt, sin, cos) + 5 FMUL + 1 FADD per complex sample.
+// 4 MUFU (lg2, sqrt, sin, cos) + 4 FMUL + 1 FMUL2 + 1 FADD + 2 LEA.HI per complex sample.
 __device__ __forceinline__ float2 weighted_normal_m(uint32_t mr, uint32_t ma, float w) {
     const float u1 = 2.0f - __uint_as_float(0x3f800000u | mr);
     float rad;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(-1.3862943611198906f * __log2f(u1)));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(-1.3862943611198906f * lg2_ftz(u1)));
     rad *= w;
     const float ang = 6.283185307179586f * __uint_as_float(0x3f800000u | ma);
     float2 cs;

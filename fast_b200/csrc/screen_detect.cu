@@ -499,7 +499,7 @@ __global__ void __launch_bounds__(THREADS, MINB) screen_detect_radix(const __gri
 // im(2q), im(2q+1)), which pass 2 reads with one 128-bit load per element pair.
 __device__ __forceinline__ pc weighted_normal_pair(uint32_t mrA, uint32_t maA, uint32_t mrB, uint32_t maB, float2 w) {
     const float2 u1 = sub2(bc2(2.0f), make_float2(__uint_as_float(0x3f800000u | mrA), __uint_as_float(0x3f800000u | mrB)));
-    const float2 r2 = mul2(make_float2(__log2f(u1.x), __log2f(u1.y)), bc2(-1.3862943611198906f));
+    const float2 r2 = mul2(make_float2(lg2_ftz(u1.x), lg2_ftz(u1.y)), bc2(-1.3862943611198906f));
     float2 rad;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad.x) : "f"(r2.x));
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad.y) : "f"(r2.y));
