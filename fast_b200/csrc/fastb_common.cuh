@@ -79,6 +79,20 @@ __device__ __forceinline__ float2 weighted_normal_m(uint32_t mr, uint32_t ma, fl
     return mul2(cs, bc2(rad));            // (rad cos, rad sin): one FMUL2 with a broadcast operand
 }
 
+// The same sample for a weight that already carries the factor sqrt(2 ln 2) (kBoxMullerScale):
+// radius = sqrt(-log2 u1) * ws, one multiply less per sample.
+constexpr float kBoxMullerScale = 1.1774100225154747f;
+__device__ __forceinline__ float2 weighted_normal_s(uint32_t mr, uint32_t ma, float ws) {
+    const float u1 = 2.0f - __uint_as_float(0x3f800000u | mr);
+    float rad;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(-lg2_ftz(u1)));
+    rad *= ws;
+    const float ang = 6.283185307179586f * __uint_as_float(0x3f800000u | ma);
+    float2 cs;
+    __sincosf(ang, &cs.y, &cs.x);
+    return mul2(cs, bc2(rad));
+}
+
 // top 23 bits of each word (used by the chi and sub-harmonic streams)
 __device__ __forceinline__ float2 box_muller(uint32_t wa, uint32_t wb) {
     return weighted_normal_m(wa >> 9, wb >> 9, 1.0f);

@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(THREADS, MINB) screen_detect_radix(const __gri
                                 const float fa = __uint_as_float(0x3f800000u | ma[j]) - 1.5f;
                                 v[m] = make_float2(fr * w[m], fa * w[m]);
                             } else {
-                                v[m] = weighted_normal_m(mr[j], ma[j], w[m]);
+                                v[m] = weighted_normal_s(mr[j], ma[j], w[m]);     // a.weight is pre-scaled here
                             }
                         }
                     }
@@ -779,6 +779,12 @@ __global__ void __launch_bounds__(kThreads) screen_detect_direct(const __grid_co
     }
 }
 
+// weight * sqrt(2 ln 2) for the radix kernel's device-RNG path (weighted_normal_s)
+__global__ void scale_weight_kernel(const float* __restrict__ w, float* __restrict__ out, long long n2) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n2) out[i] = w[i] * kBoxMullerScale;
+}
+
 __global__ void transpose_u_kernel(const float* __restrict__ U, int P, float* __restrict__ u_t) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P * P) return;
@@ -1055,7 +1061,8 @@ extern "C" int64_t fastb_screen_detect_workspace_bytes(const FastbRunParams* p) 
     long long grid = (long long)sms * kMaxCtasPerSm;
     if (grid > p->n_pairs) grid = p->n_pairs;
     if (grid < 1) grid = 1;
-    const size_t ut = align_up(sizeof(float) * (size_t)(p->n_pup + 1) * p->n_pup, 256);
+    const size_t ut = align_up(sizeof(float) * (size_t)(p->n_pup + 1) * p->n_pup, 256) +
+                      align_up(sizeof(float) * (size_t)p->n * p->n, 256);
     return (int64_t)(ut + (size_t)grid * p->n * (p->n_pup + 1) * sizeof(float2));
 }
 
@@ -1070,8 +1077,10 @@ extern "C" int fastb_screen_detect(const FastbRunParams* p, const float* d_weigh
                   "fastb_screen_detect: d_weight must be 16-byte and d_workspace 256-byte aligned");
     if (p->n_pairs == 0) return FASTB_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    // [U table: transposed (P*P) or pair-interleaved ((P+1)*P) | scratch slots of N*(P+1) complex]
-    const size_t ut = align_up(sizeof(float) * (size_t)(p->n_pup + 1) * p->n_pup, 256);
+    // [U table: transposed (P*P) or pair-interleaved ((P+1)*P) | weight * sqrt(2 ln 2) (N*N, radix
+    //  kernel with device RNG) | scratch slots of N*(P+1) complex]
+    const size_t ut0 = align_up(sizeof(float) * (size_t)(p->n_pup + 1) * p->n_pup, 256);
+    const size_t ut = ut0 + align_up(sizeof(float) * (size_t)p->n * p->n, 256);
     const size_t slot = (size_t)p->n * (p->n_pup + 1) * sizeof(float2);
     FASTB_REQUIRE(workspace_bytes >= (int64_t)(ut + slot), "fastb_screen_detect: workspace too small (%lld B)",
                   (long long)workspace_bytes);
@@ -1141,6 +1150,13 @@ extern "C" int fastb_screen_detect(const FastbRunParams* p, const float* d_weigh
 
     const bool use_radix = p->algo == FASTB_ALGO_RADIX || (p->algo == FASTB_ALGO_AUTO && radix_ok(p->n));
     if (use_radix) {
+        if (rng) {
+            float* scaled = (float*)((char*)d_workspace + ut0);
+            const long long n2 = (long long)p->n * p->n;
+            scale_weight_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(d_weight, scaled, n2);
+            if ((rc = check_launch("scale_weight_kernel"))) return rc;
+            a.weight = scaled;
+        }
         switch (p->n) {
             case 64: return launch_radix<6>(a, rng, (int)max_grid, st);
             case 128: return launch_radix<7>(a, rng, (int)max_grid, st);
