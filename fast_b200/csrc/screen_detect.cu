@@ -25,6 +25,9 @@ struct RunArgs {
     unsigned long long seed;
     float inv_usum, sigma_chi;
     const float* weight;      // N*N signed weight
+    float* weight_s;          // radix kernel, device RNG: weight * sqrt(2 ln 2), interleaved per thread
+                              // (workspace; written by scale_weight_kernel): element (row r, thread u,
+                              // register m) at r*N + (m/4)*(4*S1) + 4*u + m%4
     const float* u_t;         // n_pup*n_pup, transposed: u_t[c*n_pup + r]
     const float2* u_p;        // line-pair kernel: u_p[cp*n_pup + r] = (U[r][2cp], U[r][2cp+1] or 0)
     const float* chi;         // global-index log-amplitudes or NULL
@@ -382,6 +385,16 @@ __global__ void __launch_bounds__(THREADS, MINB) screen_detect_radix(const __gri
                     for (int m = 0; m < E; ++m) w[m] = ws[u + S1 * m];
                     __syncwarp();
                     if (it + 1 < n1) prefetch(it + 1);
+                } else if (RNG) {
+                    const float4* wq = reinterpret_cast<const float4*>(a.weight_s + (size_t)line * N) + u;
+#pragma unroll
+                    for (int j = 0; j < E / 4; ++j) {
+                        const float4 t = __ldg(wq + j * S1);
+                        w[4 * j] = t.x;
+                        w[4 * j + 1] = t.y;
+                        w[4 * j + 2] = t.z;
+                        w[4 * j + 3] = t.w;
+                    }
                 } else {
                     const float* wrow = a.weight + (size_t)line * N;
 #pragma unroll
@@ -414,8 +427,10 @@ __global__ void __launch_bounds__(THREADS, MINB) screen_detect_radix(const __gri
                                 const float fr = __uint_as_float(0x3f800000u | mr[j]) - 1.5f;
                                 const float fa = __uint_as_float(0x3f800000u | ma[j]) - 1.5f;
                                 v[m] = make_float2(fr * w[m], fa * w[m]);
+                            } else if (kTmaW) {
+                                v[m] = weighted_normal_m(mr[j], ma[j], w[m]);     // staged from the caller's table
                             } else {
-                                v[m] = weighted_normal_s(mr[j], ma[j], w[m]);     // a.weight is pre-scaled here
+                                v[m] = weighted_normal_s(mr[j], ma[j], w[m]);     // pre-scaled copy
                             }
                         }
                     }
@@ -779,10 +794,15 @@ __global__ void __launch_bounds__(kThreads) screen_detect_direct(const __grid_co
     }
 }
 
-// weight * sqrt(2 ln 2) for the radix kernel's device-RNG path (weighted_normal_s)
-__global__ void scale_weight_kernel(const float* __restrict__ w, float* __restrict__ out, long long n2) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n2) out[i] = w[i] * kBoxMullerScale;
+// weight * sqrt(2 ln 2) for the radix kernel's device-RNG path (weighted_normal_s), interleaved so
+// that thread u of a line fetches its registers m = 4j .. 4j+3 (cells u + S1 m) with one 128-bit load
+// per j and the threads of a line read consecutive 16-byte words
+__global__ void scale_weight_kernel(const float* __restrict__ w, float* __restrict__ out, int n, int s1) {
+    const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= (long long)n * n) return;
+    const int r = (int)(o / n), rem = (int)(o % n);
+    const int j = rem / (4 * s1), u = (rem % (4 * s1)) / 4, q = rem % 4;
+    out[o] = w[(size_t)r * n + u + s1 * (4 * j + q)] * kBoxMullerScale;
 }
 
 __global__ void transpose_u_kernel(const float* __restrict__ U, int P, float* __restrict__ u_t) {
@@ -961,6 +981,12 @@ int launch_radix_e(const RunArgs& args, bool rng, int max_grid, cudaStream_t st)
         }
     }
 #endif
+    if (rng) {
+        const long long n2 = (long long)F::N * F::N;
+        scale_weight_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(args.weight, args.weight_s, F::N, F::S1);
+        const int rc = check_launch("scale_weight_kernel");
+        if (rc) return rc;
+    }
     // N <= 512: stage two rows per line slot in shared memory and store them as one 16-byte word
     // per column (a scattered 8-byte store costs the L1 data pipe one wavefront per lane: 49 % of
     // all wavefronts at N = 256).  Same-box A/B: +1 % at N = 256, +4 % at N = 512, -2 % at N = 1024.
@@ -1099,6 +1125,7 @@ extern "C" int fastb_screen_detect(const FastbRunParams* p, const float* d_weigh
     a.inv_usum = (float)(1.0 / p->u_sum);
     a.sigma_chi = p->sigma_chi;
     a.weight = d_weight;
+    a.weight_s = nullptr;
     a.u_t = (const float*)d_workspace;
     a.u_p = (const float2*)d_workspace;
     a.chi = d_chi;
@@ -1150,13 +1177,7 @@ extern "C" int fastb_screen_detect(const FastbRunParams* p, const float* d_weigh
 
     const bool use_radix = p->algo == FASTB_ALGO_RADIX || (p->algo == FASTB_ALGO_AUTO && radix_ok(p->n));
     if (use_radix) {
-        if (rng) {
-            float* scaled = (float*)((char*)d_workspace + ut0);
-            const long long n2 = (long long)p->n * p->n;
-            scale_weight_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(d_weight, scaled, n2);
-            if ((rc = check_launch("scale_weight_kernel"))) return rc;
-            a.weight = scaled;
-        }
+        a.weight_s = (float*)((char*)d_workspace + ut0);      // filled by launch_radix_e when rng
         switch (p->n) {
             case 64: return launch_radix<6>(a, rng, (int)max_grid, st);
             case 128: return launch_radix<7>(a, rng, (int)max_grid, st);
