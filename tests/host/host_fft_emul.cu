@@ -143,7 +143,41 @@ double run_32(unsigned seed) {
     return check(x, X, seen, 1, label);
 }
 
+// keep_mask<F>(half) (compile-time output pruning) against a brute-force scan of k_out, and the
+// register counts DESIGN.md quotes for the bench crops
+template <int LOG2N>
+int check_keep_masks() {
+    using F = LineFFT<LOG2N, float2>;
+    constexpr int N = F::N;
+    int bad = 0;
+    const int halves[3] = {N / 8, 3 * N / 16, N / 4};
+    constexpr unsigned m1 = keep_mask<F>(N / 8), m2 = keep_mask<F>(3 * N / 16), m3 = keep_mask<F>(N / 4);
+    const unsigned got[3] = {m1, m2, m3};
+    for (int i = 0; i < 3; ++i) {
+        unsigned want = 0;
+        for (int u = 0; u < F::S1; ++u)
+            for (int e = 0; e < 16; ++e) {
+                const int k = F::k_out(u, e);
+                if (k >= N / 2 - halves[i] && k < N / 2 + halves[i]) want |= 1u << e;
+            }
+        if (want != got[i]) ++bad;
+        printf("N=%d window half=%d keeps %d of 16 registers (mask 0x%04x)%s\n", N, halves[i],
+               __builtin_popcount(got[i]), got[i], want == got[i] ? "" : "  MISMATCH");
+    }
+    if ((m1 & ~m2) || (m2 & ~m3)) ++bad;          // nested windows -> nested masks
+    return bad;
+}
+
 int main() {
+    int bad = check_keep_masks<6>() + check_keep_masks<7>() + check_keep_masks<8>() + check_keep_masks<9>() +
+              check_keep_masks<10>() + check_keep_masks<11>();
+    if (__builtin_popcount(keep_mask<LineFFT<8, float2>>(48)) != 6) ++bad;     // C2: 82 of 256 -> 6 of 16
+    if (__builtin_popcount(keep_mask<LineFFT<9, float2>>(96)) != 6) ++bad;     // C4: 162 of 512 -> 6 of 16
+    if (__builtin_popcount(keep_mask<LineFFT<10, float2>>(128)) != 4) ++bad;   // C5: 162 of 1024 -> 4 of 16
+    if (bad) {
+        printf("keep_mask check failed (%d)\n", bad);
+        return 2;
+    }
     double w = 0;
     w = fmax(w, run_one<6, float2>(1));
     w = fmax(w, run_one<7, float2>(2));

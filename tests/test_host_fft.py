@@ -1,5 +1,6 @@
 """Runs the CPU emulation of the device line FFT (tests/host/host_fft_emul.cu): the exact
-per-thread phases of fast_b200/csrc/fft_core.cuh against a float64 DFT for N = 64..2048."""
+per-thread phases of fast_b200/csrc/fft_core.cuh against a float64 DFT for N = 64..2048, and the
+constexpr register masks of the window-specialised kernel instances."""
 import os
 import shutil
 import subprocess
@@ -17,3 +18,5 @@ def test_line_fft_index_algebra(tmp_path):
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout
     assert out.stdout.count('max_err') == 14
+    # compile-time output pruning: keep_mask<F>() equals a brute-force scan for 6 sizes x 3 window classes
+    assert out.stdout.count('keeps') == 18 and 'MISMATCH' not in out.stdout
