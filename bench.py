@@ -2,16 +2,28 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c4|c5]
 
-One "step" = one pass of the hot path over one batch of the named workload on every rank:
-K2 (noise -> screens -> detector, fastb_screen_detect) + K3 (fastb_stats) + the all-reduce of
-moments/histogram (N > 1).  Weak scaling: every rank processes a full batch of its own
-realisation range.  Prints ONE JSON line on rank 0 (contract: see the task statement / DESIGN.md).
+One "step" = one pass of the hot path over one batch of the named workload on every rank: ONE K2
+launch (noise -> screens -> detector with the result statistics fused into its epilogue,
+fastb_screen_detect_batch) followed, at N > 1, by ONE small collective that combines the ranks'
+moments / extrema / histogram.  Weak scaling: every rank processes a full batch of its own
+realisation range.  The batch is sized so that a step is >= 100 ms of GPU work (C2: 12 x the
+config's 1e5 realisations).  Prints ONE JSON line on rank 0 (contract: task statement / DESIGN.md):
+
+  value         device-timed throughput of the steps (CUDA events, L2 flushed between steps, max over ranks)
+  e2e           the same workload through the public object: host weight/U -> device, Fast(p).run() ->
+                host result.power, wall clock (includes the all-gather at N > 1)
+  roofline      model-A HBM figure of the K2 kernel + the instruction-issue ceiling (secondary)
+  per_workload  every configuration of BASELINE.json (C1 TEMPORAL, C1' N=164, C2, C3 batched sweep, C4, C5,
+                C5 strong-scaled over the ranks), each with its own kernel time and roofline fraction
+  check         run-time correctness: statistics of the timed steps; at N > 1 the sharded run is compared
+                bit for bit with an unsharded one
 
 --impl reference times the reference's CPU algorithm (the numpy oracle port of
 fast/fast.py:115-140,589-668: /root/reference is pure Python and cannot travel to the GPU box)
 on all host cores, on bounded samples of the same workload.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -26,12 +38,13 @@ if ROOT not in sys.path:
 METRIC = "MC realizations/sec (screen+detect)"
 UNIT = "realizations/s"
 
+# name: (config factory, realisations per step per GPU, N, n_pup, description)
 WORKLOADS = {
-    # name: (config factory, realisations per step per GPU, description)
-    'c2': ('c2', 100000, "C2: GEO ground-station downlink, 256x256 grid, 1e5 realizations per step per GPU, "
-                         "AO residual PSD + scintillation, SMF detection"),
-    'c4': ('c4', 100000, "C4: coherent detection, 512x512 grid, 1e5 realizations per step per GPU"),
-    'c5': ('c5', 20000, "C5 shard: 1024x1024 grid, 2e4 realizations per step per GPU"),
+    'c2': ('c2', 1200000, 256, 82,
+           "C2: GEO ground-station downlink, 256x256 grid, AO residual PSD + scintillation, SMF detection; "
+           "1.2e6 realizations per step per GPU (12 x the config's 1e5, so that a step is >= 100 ms)"),
+    'c4': ('c4', 300000, 512, 162, "C4: coherent detection, 512x512 grid, 3e5 realizations per step per GPU"),
+    'c5': ('c5', 80000, 1024, 162, "C5 shard: 1024x1024 grid, 8e4 realizations per step per GPU"),
 }
 
 
@@ -49,6 +62,44 @@ def measured_peak():
         except Exception:
             pass
     return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def kernel_digest():
+    """sha256 over the K2 device sources: the ncu-derived counters in profiles/ are only used when they
+    were captured from exactly these sources."""
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, 'fast_b200', 'csrc')
+    for f in ('fastb_common.cuh', 'fft_core.cuh', 'screen_detect_kernel.cuh', 'screen_detect_radix.cu',
+              'screen_detect_bluestein.cu', 'screen_detect.cu'):
+        with open(os.path.join(d, f), 'rb') as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def ncu_counters(workload):
+    """Per-pair counters of the K2 kernel from the committed ncu capture of this round
+    (profiles/kernel_counters_r02.json, written by tools/ncu_counters.py): DRAM bytes and executed warp
+    instructions.  Returns (dict | None, note): None when there is no capture of the current sources."""
+    path = os.path.join(ROOT, 'profiles', 'kernel_counters_r02.json')
+    try:
+        rec = json.load(open(path))
+    except Exception:
+        return None, 'no ncu capture committed'
+    w = rec.get('workloads', {}).get(workload)
+    if not w:
+        return None, 'no ncu capture for this workload'
+    if rec.get('kernel_digest') != kernel_digest():
+        return None, f"ncu capture is of other kernel sources ({rec.get('kernel_digest')}): not used"
+    return w, 'ncu --set full capture of these sources (profiles/kernel_counters_r02.json)'
+
+
+def config_of(workload, world):
+    factory, n_real, N, P, desc = WORKLOADS[workload]
+    return {"workload": desc, "N": N, "n_pup": P, "layers": 4, "realizations_per_step_per_gpu": n_real,
+            "rng": "device Philox4x32-10 + Box-Muller",
+            "l2": "flushed (256 MiB write) between timed steps",
+            "parallelism": f"realization ranges sharded over {world} GPU(s), moments+histogram combined by one "
+                           "collective per step"}
 
 
 class ClockSampler(threading.Thread):
@@ -111,7 +162,7 @@ _W = {}
 def _cpu_worker_init(workload, seed_base):
     import numpy as np
     from oracle import configs, fast_oracle as fo
-    factory, _, _ = WORKLOADS[workload]
+    factory = WORKLOADS[workload][0]
     p = getattr(configs, factory)(niter=2, nchunks=1)
     _W['init'] = fo.build(p)
     _W['fo'] = fo
@@ -134,7 +185,7 @@ def _cpu_worker_step(n_real):
 def cpu_psd_build_seconds(workload):
     """Wall time of the oracle's whole init (PSD build dominated by the aliasing sum), 1 core."""
     from oracle import configs, fast_oracle as fo
-    factory, _, _ = WORKLOADS[workload]
+    factory = WORKLOADS[workload][0]
     p = getattr(configs, factory)(niter=2, nchunks=1)
     t0 = time.perf_counter()
     fo.build(p)
@@ -159,7 +210,7 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    factory, n_real, desc = WORKLOADS[args.workload]
+    world = int(os.environ.get('WORLD_SIZE', str(args.gpus)))
     cores = min(os.cpu_count() or 1, 128)
     rate_guess = {'c2': 200.0, 'c4': 45.0, 'c5': 10.0}[args.workload]
     budget = 150.0 / max(1, args.steps + args.warmup)              # seconds per step
@@ -169,7 +220,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": {"workload": desc, "sample": sample},
+            "data": "synthetic", "config": config_of(args.workload, world),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -279,6 +330,216 @@ def k5_link_metrics(with_cpu):
     return out
 
 
+# ------------------------------------------------------------------------- GPU
+class DramSampler:
+    """DRAM bandwidth utilisation of the timed region from NVML's GPM counters (Hopper and later),
+    when the driver exposes them: a measured-in-run figure beside the ncu capture."""
+
+    def __init__(self, index):
+        self.ok, self.note = False, None
+        try:
+            import pynvml as nv
+            self.nv = nv
+            nv.nvmlInit()
+            self.h = nv.nvmlDeviceGetHandleByIndex(index)
+            sup = nv.nvmlGpmQueryDeviceSupport(self.h)
+            if not sup.isSupportedDevice:
+                raise RuntimeError('GPM not supported')
+            self.s0, self.s1 = nv.nvmlGpmSampleAlloc(), nv.nvmlGpmSampleAlloc()
+            self.ok = True
+        except Exception as e:
+            self.note = f'GPM unavailable ({type(e).__name__}: {e})'
+
+    def start(self):
+        if self.ok:
+            try:
+                self.nv.nvmlGpmSampleGet(self.h, self.s0)
+            except Exception as e:
+                self.ok, self.note = False, f'GPM sample failed ({type(e).__name__})'
+
+    def stop(self):
+        """-> percent of peak DRAM bandwidth over the region, or None."""
+        if not self.ok:
+            return None
+        try:
+            nv = self.nv
+            nv.nvmlGpmSampleGet(self.h, self.s1)
+            mg = nv.c_nvmlGpmMetricsGet_t()
+            mg.version = nv.NVML_GPM_METRICS_GET_VERSION
+            mg.numMetrics = 1
+            mg.sample1, mg.sample2 = self.s0, self.s1
+            mg.metrics[0].metricId = nv.NVML_GPM_METRIC_DRAM_BW_UTIL
+            nv.nvmlGpmMetricsGet(mg)
+            return float(mg.metrics[0].value)
+        except Exception as e:
+            self.note = f'GPM read failed ({type(e).__name__}: {e})'
+            return None
+
+
+def timed_launches(sim, n_real, reps, flush, sb=None, first_base=0):
+    """Median device time [ms] of `reps` K2 launches of n_real realisations (L2 flushed before each)."""
+    import torch
+    n_pairs = n_real // 2
+    sim.screen_detect(first_base, min(n_pairs, 20000), stats=sb)          # warm-up (+ table preparation)
+    ms = []
+    for r in range(reps):
+        flush.fill_(r & 0xFF)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        sim.screen_detect(first_base + (r + 1) * n_pairs, n_pairs, stats=sb)
+        e1.record()
+        e1.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    ms.sort()
+    return ms[len(ms) // 2]
+
+
+def per_workload(world, rank, flush, peak, dev):
+    """Every configuration of BASELINE.json on this box, outside the headline's timed region: a few
+    launches each (CUDA events, L2 flushed), model-A roofline fraction of its own kernel time."""
+    import torch
+    import torch.distributed as td
+    import fast_b200
+    from fast_b200 import configs, dist, sweep
+    out = {}
+
+    def entry(name, n_real, ms, N, coherent, kernel, note=None, gpus=1):
+        b_alg = algorithmic_bytes(N, coherent)
+        v = n_real / (ms * 1e-3)
+        counters, cnote = ncu_counters(name)
+        e = {"value": v, "unit": UNIT, "n_gpus": gpus, "realizations_per_launch_per_gpu": n_real // gpus,
+             "kernel": kernel, "kernel_ms": ms, "N": N,
+             "roofline_frac": b_alg * v / gpus / 1e9 / peak, "algorithmic_bytes_per_realization": b_alg,
+             "dram_bytes_per_launch": (counters['dram_bytes_per_pair'] * (n_real // gpus // 2)) if counters else None,
+             "dram_bytes_source": cnote}
+        if note:
+            e["note"] = note
+        out[name] = e
+
+    def sync_max(ms):
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            td.all_reduce(t, op=td.ReduceOp.MAX)
+        return float(t.item())
+
+    if world == 1:
+        # C1 verbatim: TEMPORAL frozen flow, N = 164 (auto), 100 time steps per run
+        sim = fast_b200.Fast(configs.c1(seed=1))
+        sim.run()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        reps = 10
+        for _ in range(reps):
+            sim.run()
+        dt = (time.perf_counter() - t0) / reps
+        out['c1_temporal'] = {"value": sim.Niter / dt, "unit": "time steps/s", "n_gpus": 1, "N": sim.Npxls,
+                              "run_ms": 1e3 * dt, "kernel": "screens_rows/cols_kernel + temporal_detect_kernel",
+                              "note": "test/test_params.py verbatim: wall time of Fast.run() (layer screens + 10 chunks "
+                                      "of 10 steps + host coordinate bookkeeping), latency-bound at this size"}
+        # C1': same grid, TEMPORAL off -> the chirp-z kernel (N = 164 is not a power of two)
+        n_real = 200000
+        sim = fast_b200.Fast(configs.c1prime(niter=n_real, nchunks=1, seed=1))
+        ms = timed_launches(sim, n_real, 3, flush)
+        entry('c1prime', n_real, ms, sim.Npxls, False, 'screen_detect_bluestein<M=256>')
+        # the O(N^2)-per-line direct kernel on the same grid, for scale
+        from fast_b200 import _lib
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sim.screen_detect(0, 2000, algo=_lib.ALGO_DIRECT)
+        e0.record()
+        sim.screen_detect(0, 10000, algo=_lib.ALGO_DIRECT)
+        e1.record()
+        e1.synchronize()
+        out['c1prime']['direct_dft_value'] = 20000 / (e0.elapsed_time(e1) * 1e-3)
+        for name, factory, n_real, kern in (('c2', 'c2', 1200000, 'screen_detect_radix<N=256, window 2>'),
+                                            ('c4', 'c4', 300000, 'screen_detect_radix<N=512, window 2>'),
+                                            ('c5', 'c5', 80000, 'screen_detect_radix<N=1024, window 1>')):
+            p = getattr(configs, factory)(niter=n_real, nchunks=1, seed=1)
+            sim = fast_b200.Fast(dict(p))
+            sb = dist.StatsBuffers(4096, dev)
+            ms = timed_launches(sim, n_real, 3, flush, sb)
+            entry(name, n_real, ms, sim.Npxls, bool(p['COHERENT']), kern)
+            if name == 'c2':
+                simf = fast_b200.Fast(dict(p, RNG='device-fast'))
+                msf = timed_launches(simf, n_real, 3, flush, sb)
+                entry('c2_device_fast', n_real, msf, sim.Npxls, False, kern + ', RNG device-fast',
+                      note="opt-in RNG='device-fast' (Philox4x32-7, 40 bits per complex sample)")
+            del sim
+    # C3: 16 elevations x 1e4 realisations as ONE batched launch, (elevation x pair) sharded over the ranks
+    ps = [configs.c3_elevation(e, niter=10000, nchunks=1, seed=100 + i) for i, e in enumerate(configs.C3_ELEVATIONS)]
+    sims = sweep.build_sims(ps)
+    sweep.run_sweep(sims)                                  # warm-up
+    torch.cuda.synchronize()
+    if world > 1:
+        td.barrier()
+    flush.fill_(3)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    res = sweep.run_sweep(sims, stats=True)
+    e1.record()
+    e1.synchronize()
+    wall = time.perf_counter() - t0
+    ms = sync_max(e0.elapsed_time(e1))
+    if rank == 0:
+        entry('c3_sweep', 160000, ms, 256, False, 'screen_detect_radix<N=256, window 2>, 16-item batch',
+              note="device time of sweep.run_sweep: stack weights, ONE K2 launch over 16 x 5000 pairs, statistics "
+                   "all-gather, result all-gather, D2H; per-elevation mean dB_rel in mean_db", gpus=world)
+        out['c3_sweep']['wall_ms'] = 1e3 * wall
+        out['c3_sweep']['mean_db'] = [round(float(r.dB_rel.mean()), 3) for r in res]
+    # C5 as BASELINE.json states it: 1e6 realisations in total, strong-scaled over the ranks, one collective
+    total = 1000000
+    p = configs.c5(niter=total, nchunks=1, seed=1)
+    sim = fast_b200.Fast(dict(p))
+    sb = dist.StatsBuffers(4096, dev)
+    lo, hi = dist.shard_range(total // 2, rank, world)
+    sim.screen_detect(lo, min(hi - lo, 2000), stats=sb)
+    sb.reset()
+    torch.cuda.synchronize()
+    if world > 1:
+        td.barrier()
+    flush.fill_(5)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    sim.screen_detect(lo, hi - lo, stats=sb)
+    sb.allreduce()
+    e1.record()
+    e1.synchronize()
+    ms = sync_max(e0.elapsed_time(e1))
+    if rank == 0:
+        entry('c5_strong', total, ms, 1024, False, 'screen_detect_radix<N=1024, window 1>',
+              note=f"1e6 realizations in total sharded over {world} GPU(s), fused statistics + one collective", gpus=world)
+        st = sb.summary()
+        out['c5_strong']['n_reduced'] = st['n']
+        out['c5_strong']['mean_db'] = st['mean_dB']
+    return out
+
+
+def sharded_check(world, rank, dev):
+    """N > 1: Fast.run() sharded over the ranks (+ all-gather) against the same global pair range
+    computed unsharded on every rank: must be bit-identical (tests/multi_gpu_check.py, run here too so
+    that the driver's scaling runs carry the evidence)."""
+    import numpy as np
+    import torch
+    import torch.distributed as td
+    import fast_b200
+    from fast_b200 import configs, dist
+    ok = True
+    for factory, kw in (('mini', dict(niter=2000, nchunks=4, seed=4)),
+                        ('mini', dict(niter=2002, nchunks=1, seed=4, COHERENT=True)),
+                        ('c2', dict(niter=6000, nchunks=3, seed=8)),
+                        ('c1prime', dict(niter=600, nchunks=2, seed=9))):
+        p = getattr(configs, factory)(**kw)
+        sim = fast_b200.Fast(dict(p))
+        r_sharded = sim.run()._r
+        ppc = sim.Niter_per_chunk // 2
+        a, b = sim.screen_detect(0, sim.Nchunks * ppc)
+        r_single = dist.assemble(a, b, sim.Nchunks, ppc).cpu().numpy()
+        ok = ok and bool(np.array_equal(r_sharded, r_single.astype(r_sharded.dtype)))
+    t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+    td.all_reduce(t, op=td.ReduceOp.MIN)
+    return bool(t.item())
+
+
 def run_ours(args):
     import torch
     import torch.distributed as td
@@ -295,8 +556,9 @@ def run_ours(args):
     from fast_b200 import _lib, dist
     from fast_b200 import configs
 
-    factory, n_real, desc = WORKLOADS[args.workload]
-    p = getattr(configs, factory)(niter=n_real, nchunks=1, seed=1)
+    factory, n_real, _, _, desc = WORKLOADS[args.workload]
+    # the public object: NITER = the whole job of one step (world x n_real), sharded by Fast.run()
+    p = getattr(configs, factory)(niter=world * n_real, nchunks=1, seed=1)
     sim = fast_b200.Fast(dict(p))
     N, P = sim.Npxls, sim.Npxls_pup
     coherent = bool(p['COHERENT'])
@@ -304,22 +566,18 @@ def run_ours(args):
     dev = sim.device
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
     nbins = 4096
+    sb = dist.StatsBuffers(nbins, dev)
 
     def step(i, k2_events=None):
         # rank r, step i -> its own range of global pair indices (no overlap across ranks/steps)
         first = (i * world + rank) * n_pairs
+        sb.reset()
         if k2_events is not None:
             k2_events[0].record()
-        a, b = sim.screen_detect(first, n_pairs)
+        sim.screen_detect(first, n_pairs, stats=sb)          # ONE launch: K2 with the statistics fused
         if k2_events is not None:
             k2_events[1].record()
-        r = torch.cat([a, b])
-        if r.is_complex():
-            r = (r.real ** 2 + r.imag ** 2)
-        sums, minmax, hist = dist.new_stats_buffers(nbins, dev)
-        _lib.stats(r.contiguous(), -60.0, 3.0, nbins, sums, minmax, hist)
-        dist.allreduce_stats(sums, minmax, hist)
-        return sums
+        sb.allreduce()                                       # ONE collective (no-op on a single rank)
 
     for i in range(args.warmup):
         step(i)
@@ -333,31 +591,38 @@ def run_ours(args):
         sim.compute_powerspec()
         torch.cuda.synchronize()
         k1_ms.append(1e3 * (time.perf_counter() - t0))
+    step(0)                                                  # tables re-prepared for the rebuilt weight
+    torch.cuda.synchronize()
 
     sampler = ClockSampler(local)
     sampler.start()
+    dram = DramSampler(local)
     if world > 1:
         td.barrier()
     torch.cuda.synchronize()
     _lib.reset_launch_count()
-    launches_torch = 0
+    dram.start()
+    t_region = time.perf_counter()
     step_ms, k2_ms = [], []
     for i in range(args.steps):
         flush.fill_(i & 0xFF)                                            # evict L2 between steps
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        sums = step(args.warmup + i, (k0, k1))
+        step(args.warmup + i, (k0, k1))
         e1.record()
         e1.synchronize()
         step_ms.append(e0.elapsed_time(e1))
         k2_ms.append(k0.elapsed_time(k1))
     torch.cuda.synchronize()
+    t_region = time.perf_counter() - t_region
+    dram_util = dram.stop()
     if world > 1:
         td.barrier()
     launches = _lib.launch_count()
     sampler.stop_flag = True
     sampler.join(timeout=2)
+    stats_last = sb.summary()
 
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -365,52 +630,55 @@ def run_ours(args):
     total_ms = float(total_ms.item())
     value = world * n_real * args.steps / (total_ms * 1e-3)
 
-    # ---- end to end through the public object, host buffers in, host results out ----
+    # ---- end to end through the public object: pinned host weight / U in, host result.power out ----
     w_host = sim._d['weight'].cpu().pin_memory()
     u_host = sim._d['U'].cpu().pin_memory()
     width = 2 if coherent else 1
-    out_host = torch.empty(n_real * width, dtype=torch.float32).pin_memory()
     h2d = w_host.numel() * 4 + u_host.numel() * 4
-    d2h = out_host.numel() * 4
+    d2h = world * n_real * width * 4           # Fast.run() leaves the WHOLE result array on every rank
 
-    def e2e_step(i):
+    def e2e_step():
         sim._d['weight'].copy_(w_host, non_blocking=True)
         sim._d['U'].copy_(u_host, non_blocking=True)
-        first = (i * world + rank) * n_pairs
-        a, b = sim.screen_detect(first, n_pairs)
-        flat = dist.assemble(a, b, 1, n_pairs)
-        src = torch.view_as_real(flat).reshape(-1) if flat.is_complex() else flat
-        out_host.copy_(src, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        res = sim.run()                        # fast/fast.py:115-140 contract: FastResult on the host
+        return res.power
 
-    e2e_step(0)
+    power = e2e_step()
     if world > 1:
         td.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for i in range(args.steps):
-        e2e_step(1000 + i)
+    e2e_steps = max(3, args.steps // 2)
+    for _ in range(e2e_steps):
+        power = e2e_step()
     torch.cuda.synchronize()
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
         td.all_reduce(e2e_s, op=td.ReduceOp.MAX)
-    e2e_value = world * n_real * args.steps / float(e2e_s.item())
+    e2e_value = world * n_real * e2e_steps / float(e2e_s.item())
+    e2e_ok = bool(power.shape == (world * n_real,) and (abs(power) > 0).all())
+
+    peak, peak_src = measured_peak()
+    sharded_ok = sharded_check(world, rank, dev) if world > 1 else None
+    pw = None if args.no_per_workload else per_workload(world, rank, flush, peak, dev)
 
     if rank == 0:
-        peak, peak_src = measured_peak()
         b_alg = algorithmic_bytes(N, coherent)
         k2_avg_ms = sum(k2_ms) / len(k2_ms)
         achieved = b_alg * n_real / (k2_avg_ms * 1e-3) / 1e9
-        traffic = None
-        tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
-        if os.path.exists(tpath):
-            try:
-                traffic = json.load(open(tpath)).get(args.workload)
-            except Exception:
-                traffic = None
+        counters, cnote = ncu_counters(args.workload)
+        clocks = sampler.summary()
+        sm_mhz = clocks['sm_mhz'] or 1965
+        secondary = None
+        if counters:
+            ginst = counters['warp_inst_per_pair'] * n_pairs / (k2_avg_ms * 1e-3) / 1e9
+            peak_inst = 148 * 4 * sm_mhz * 1e6 / 1e9
+            secondary = {"bound": "issue", "achieved_ginst_s": ginst, "peak_ginst_s": peak_inst,
+                         "frac": ginst / peak_inst, "warp_inst_per_pair": counters['warp_inst_per_pair'],
+                         "peak_def": f"148 SMs x 4 warp-instructions/clk x {sm_mhz} MHz (clock sampled in this run)"}
         comparator = None
         if world == 1 and not args.no_comparator and not coherent:
-            comparator = cufft_comparator(sim, n_real, max(2, args.steps // 4))
+            comparator = cufft_comparator(sim, 100000, 3)
         k5 = k5_link_metrics(not args.no_cpu) if world == 1 and not args.no_comparator else None
         cpu = None
         if world == 1 and not args.no_cpu:
@@ -423,25 +691,35 @@ def run_ours(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": desc, "N": N, "n_pup": P, "layers": len(sim.h),
-                           "realizations_per_step_per_gpu": n_real, "rng": "device Philox4x32-10 + Box-Muller",
-                           "l2": "flushed (256 MiB write) between timed steps",
-                           "parallelism": f"realization ranges sharded over {world} GPU(s), "
-                                          "moments+histogram all-reduce per step"},
+                "config": config_of(args.workload, world),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                             "frac": achieved / peak,
+                             "traffic": (counters['dram_bytes_per_pair'] * n_pairs) if counters else None,
+                             "traffic_source": cnote,
+                             "dram_bw_util_pct_gpm": dram_util, "dram_bw_util_note": dram.note or
+                             "NVML GPM DRAM_BW_UTIL over the timed region (includes the L2-flush writes between steps)",
+                             "peak_source": peak_src,
                              "kernel": "screen_detect_radix", "kernel_ms": k2_avg_ms,
                              "algorithmic_bytes_per_realization": b_alg,
-                             "realizations_per_launch": n_real},
+                             "realizations_per_launch": n_real,
+                             "secondary": secondary},
                 "cpu_baseline": cpu,
                 "comparator": comparator,
                 "k1_psd_build": {"compute_powerspec_ms": min(k1_ms), "note": "K1 + Simpson + pupil filter incl. host glue; "
                                  "CPU counterpart is cpu_baseline.psd_build_s"},
                 "k5_link_metrics": k5,
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "per_workload": pw,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "steps": e2e_steps,
+                        "what": "wall clock of: pinned host weight + U -> device, fast_b200.Fast(p).run() "
+                                "(table preparation, K2, all-gather at N > 1, reference-order assembly, D2H through "
+                                "pinned memory, float64 host array) -> result.power"},
                 "gpu_launches": int(launches),
-                "clocks": sampler.summary(),
-                "check": {"mean_r": float(sums[1] / sums[0]), "n_reduced": int(sums[0])}}
+                "clocks": clocks,
+                "timed_region_s": t_region,
+                "check": {"mean_r": stats_last['mean'], "mean_db": stats_last['mean_dB'],
+                          "n_reduced": stats_last['n'], "e2e_result_ok": e2e_ok,
+                          "sharded_bit_identical": sharded_ok}}
         print(json.dumps(line), flush=True)
     if world > 1:
         td.destroy_process_group()
@@ -455,7 +733,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
-    ap.add_argument('--no-comparator', action='store_true', help='skip the cuFFT comparator leg')
+    ap.add_argument('--no-comparator', action='store_true', help='skip the cuFFT comparator and K5 legs')
+    ap.add_argument('--no-per-workload', action='store_true', help='skip the per_workload block')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'ours':
         args.warmup = 3

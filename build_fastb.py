@@ -18,25 +18,37 @@ STAMP = os.path.join(HERE, 'build', 'libfastb.stamp')
 ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
 COMMON = ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']
 # per-file extra flags: the PSD kernel follows numpy's operation order (no FMA contraction)
+_DBG = ['-DFASTB_TUNE_DBG'] if os.environ.get('FASTB_TUNE_DBG') else []
+# object name -> (source, extra flags).  The radix kernels of K2 are compiled once per grid size
+# (N = 2^6 .. 2^11) so that the ~20 instances of each size build in parallel.
 SOURCES = {
-    'api.cu': [],
-    'psd_build.cu': ['-fmad=false'],
-    'screen_detect.cu': ['-Xptxas', '-v'] + (['-DFASTB_TUNE'] if os.environ.get('FASTB_TUNE') else []) + (['-DFASTB_TUNE_DBG'] if os.environ.get('FASTB_TUNE_DBG') else []),
-    'stats.cu': [],
-    'link_metrics.cu': ['-fmad=false'],
-    'temporal.cu': [],
+    'api': ('api.cu', []),
+    'psd_build': ('psd_build.cu', ['-fmad=false']),
+    'screen_detect': ('screen_detect.cu', ['-Xptxas', '-v'] + _DBG),
+    'screen_detect_bluestein': ('screen_detect_bluestein.cu', ['-Xptxas', '-v'] + _DBG),
+    'stats': ('stats.cu', []),
+    'link_metrics': ('link_metrics.cu', ['-fmad=false']),
+    'temporal': ('temporal.cu', []),
 }
+for _k in range(6, 12):
+    SOURCES[f'screen_detect_radix_{_k}'] = ('screen_detect_radix.cu', ['-Xptxas', '-v', f'-DFASTB_LOG2N={_k}'] + _DBG)
+if os.environ.get('FASTB_TUNE'):
+    # tuning builds only: env-driven alternative kernel shapes / variants (never part of the product)
+    SOURCES['screen_detect_tune'] = (os.path.join('tune', 'screen_detect_tune.cu'), ['-Xptxas', '-v'] + _DBG)
 
 
 def _digest():
     h = hashlib.sha256()
-    for root in (CSRC, os.path.join(ROOT, 'include')):
+    for root in (CSRC, os.path.join(CSRC, 'tune'), os.path.join(ROOT, 'include')):
         for f in sorted(os.listdir(root)):
+            if os.path.isdir(os.path.join(root, f)):
+                continue
             with open(os.path.join(root, f), 'rb') as fh:
                 h.update(f.encode())
                 h.update(fh.read())
     h.update(repr(SOURCES).encode())
     h.update(os.environ.get('FASTB_TUNE', '').encode())
+    h.update(os.environ.get('FASTB_TUNE_DBG', '').encode())
     return h.hexdigest()
 
 
@@ -51,20 +63,23 @@ def build(force=False, verbose=False):
     os.makedirs(objdir, exist_ok=True)
     objs = []
     procs = []
-    for src, extra in SOURCES.items():
-        obj = os.path.join(objdir, src.replace('.cu', '.o'))
+    for name, (src, extra) in SOURCES.items():
+        obj = os.path.join(objdir, name + '.o')
         cmd = [nvcc, *ARCH, *COMMON, *extra, '-c', os.path.join(CSRC, src), '-o', obj]
-        procs.append((src, cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE,
-                                                 stderr=subprocess.STDOUT, text=True)))
+        log = open(os.path.join(objdir, name + '.log'), 'w')
+        procs.append((name, cmd, log, subprocess.Popen(cmd, stdout=log, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
-    for src, cmd, pr in procs:
-        out, _ = pr.communicate()
+    failed = None
+    for name, cmd, log, pr in procs:
+        pr.wait()
+        log.close()
+        out = open(log.name).read()
         if verbose or pr.returncode != 0:
             sys.stderr.write(out)
-        with open(os.path.join(objdir, src + '.log'), 'w') as fh:
-            fh.write(out)
-        if pr.returncode != 0:
-            raise RuntimeError(f'nvcc failed for {src}: {" ".join(cmd)}')
+        if pr.returncode != 0 and failed is None:
+            failed = f'nvcc failed for {name}: {" ".join(cmd)}'
+    if failed:
+        raise RuntimeError(failed)
     subprocess.run([nvcc, *ARCH, '-shared', '-o', LIB, *objs], check=True)
     with open(STAMP, 'w') as fh:
         fh.write(dig)

@@ -14,7 +14,8 @@ LIB_PATH = os.path.join(_HERE, 'libfastb.so')
 
 MAX_LAYERS = 32
 AO_NOAO, AO_AO, AO_LGSAO = 0, 1, 2
-ALGO_AUTO, ALGO_DIRECT, ALGO_RADIX, ALGO_RADIX_PAIR = 0, 1, 2, 3
+ALGO_AUTO, ALGO_DIRECT, ALGO_RADIX, ALGO_RADIX_PAIR, ALGO_BLUESTEIN = 0, 1, 2, 3, 4
+RUN_PREPARED, RUN_RNG_FAST = 1, 2
 
 
 class FastbError(RuntimeError):
@@ -54,10 +55,20 @@ class PsdOutputs(C.Structure):
 
 class RunParams(C.Structure):
     _fields_ = [('n', C.c_int32), ('n_pup', C.c_int32), ('lo', C.c_int32), ('coherent', C.c_int32),
-                ('algo', C.c_int32), ('reserved', C.c_int32),
+                ('algo', C.c_int32), ('flags', C.c_int32),
                 ('n_pairs', C.c_int64), ('first_pair', C.c_int64), ('pairs_per_chunk', C.c_int64),
                 ('seed', C.c_uint64), ('u_sum', C.c_double), ('sigma_chi', C.c_float),
                 ('reserved_f', C.c_float)]
+
+
+class RunBatch(C.Structure):
+    _fields_ = [('n_items', C.c_int32), ('reserved', C.c_int32), ('pairs_per_item', C.c_int64),
+                ('d_sigma_chi', C.c_void_p), ('d_seeds', C.c_void_p)]
+
+
+class RunStats(C.Structure):
+    _fields_ = [('db_lo', C.c_double), ('db_hi', C.c_double), ('nbins', C.c_int32), ('reserved', C.c_int32),
+                ('d_sums', C.c_void_p), ('d_minmax', C.c_void_p), ('d_hist', C.c_void_p)]
 
 
 class Subharm(C.Structure):
@@ -98,10 +109,18 @@ _SIGS = {
     'fastb_screen_detect': (C.c_int, [C.POINTER(RunParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.POINTER(Subharm), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                       C.c_void_p]),
+    'fastb_screen_detect_batch_workspace_bytes': (C.c_int64, [C.POINTER(RunParams), C.c_int32]),
+    'fastb_screen_detect_prepare': (C.c_int, [C.POINTER(RunParams), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                              C.c_int64, C.c_void_p]),
+    'fastb_screen_detect_batch': (C.c_int, [C.POINTER(RunParams), C.POINTER(RunBatch), C.POINTER(RunStats),
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_int64, C.c_void_p]),
     'fastb_screens_crop': (C.c_int, [C.POINTER(RunParams), C.c_void_p, C.c_void_p, C.POINTER(Subharm), C.c_void_p,
                                      C.c_void_p, C.c_int64, C.c_void_p]),
     'fastb_rng_dump': (C.c_int, [C.c_uint64, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_int64,
                                  C.c_void_p, C.c_void_p]),
+    'fastb_rng_dump_mode': (C.c_int, [C.c_uint64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int64,
+                                      C.c_void_p, C.c_void_p]),
     'fastb_layer_screens_workspace_bytes': (C.c_int64, [C.c_int32, C.c_int32]),
     'fastb_layer_screens': (C.c_int, [C.c_int32, C.c_int32, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_int64, C.c_void_p]),
@@ -225,11 +244,41 @@ def pupil_filter(pm):
     return out
 
 
-def screen_detect_workspace_bytes(rp: RunParams):
-    nbytes = lib.fastb_screen_detect_workspace_bytes(C.byref(rp))
+def screen_detect_workspace_bytes(rp: RunParams, n_items=1):
+    nbytes = lib.fastb_screen_detect_batch_workspace_bytes(C.byref(rp), int(n_items))
     if nbytes < 0:
         raise FastbError('fastb_screen_detect_workspace_bytes: ' + lib.fastb_last_error().decode())
     return int(nbytes)
+
+
+def screen_detect_prepare(rp: RunParams, weight, U, workspace, n_items=1):
+    """Fill the workspace's derived tables once (transposed U, pre-scaled weight copies / chirp
+    tables); later calls with RUN_PREPARED in rp.flags are then a single kernel launch."""
+    f32 = torch.float32
+    _check(lib.fastb_screen_detect_prepare(C.byref(rp), int(n_items), _ptr(weight, f32), _ptr(U, f32),
+                                           _ptr(workspace), workspace.numel() * workspace.element_size(),
+                                           _stream()), 'fastb_screen_detect_prepare')
+
+
+def run_stats(db_lo, db_hi, nbins, sums, minmax, hist):
+    return RunStats(db_lo=float(db_lo), db_hi=float(db_hi), nbins=int(nbins), d_sums=_ptr(sums, torch.float64),
+                    d_minmax=_ptr(minmax, torch.float64), d_hist=_ptr(hist, torch.int64))
+
+
+def screen_detect_batch(rp: RunParams, weight, U, out_a, out_b, workspace, batch=None, stats=None, chi=None):
+    """K2 with the optional batch of configurations (batch: dict(n_items, pairs_per_item, sigma_chi f32
+    tensor, seeds int64 tensor holding the uint64 bit patterns)) and the fused statistics
+    (stats: a RunStats from run_stats())."""
+    f32 = torch.float32
+    b = None
+    if batch is not None:
+        b = C.byref(RunBatch(n_items=int(batch['n_items']), pairs_per_item=int(batch['pairs_per_item']),
+                             d_sigma_chi=_ptr(batch['sigma_chi'], f32), d_seeds=_ptr(batch['seeds'], torch.int64)))
+    s = C.byref(stats) if stats is not None else None
+    _check(lib.fastb_screen_detect_batch(C.byref(rp), b, s, _ptr(weight, f32), _ptr(U, f32), _ptr(chi, f32),
+                                         _ptr(out_a, f32), _ptr(out_b, f32), _ptr(workspace),
+                                         workspace.numel() * workspace.element_size(), _stream()),
+           'fastb_screen_detect_batch')
 
 
 def screen_detect(rp: RunParams, weight, U, out_a, out_b, workspace, chi=None, noise=None, subharm=None):
@@ -258,11 +307,11 @@ def screens_crop(rp: RunParams, weight, phs, workspace, noise=None, subharm=None
            'fastb_screens_crop')
 
 
-def rng_dump(seed, pair, n, device, chi_first=0, chi_count=0, want_tile=True):
+def rng_dump(seed, pair, n, device, chi_first=0, chi_count=0, want_tile=True, fast=False):
     tile = torch.empty((n, n, 2), dtype=torch.float32, device=device) if want_tile else None
     chi = torch.empty(chi_count, dtype=torch.float32, device=device) if chi_count else None
-    _check(lib.fastb_rng_dump(int(seed), int(pair), n, _ptr(tile), int(chi_first), int(chi_count),
-                              _ptr(chi), _stream()), 'fastb_rng_dump')
+    _check(lib.fastb_rng_dump_mode(int(seed), int(pair), n, int(bool(fast)), _ptr(tile), int(chi_first),
+                                   int(chi_count), _ptr(chi), _stream()), 'fastb_rng_dump_mode')
     return tile, chi
 
 

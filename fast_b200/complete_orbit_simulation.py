@@ -159,7 +159,7 @@ def FAST_sat_orbit(fast_params, simu_params, TLE_file, geometry=None):
         p['ANISO_DL'] = aniso_dl[i, :]
         p['ZENITH_ANGLE'] = zenith
         p['AZIMUT_SAT'] = azimuts[i]
-        out[f'simulation_{i}'] = Fast(p)
+        out[f'simulation_{i}'] = Fast(dict(p))      # own copy: the sims must not share one params dict
     out['altitudes'] = altitudes
     return out
 

@@ -32,6 +32,8 @@ DEFAULTS = {
 # Keys that exist only in this implementation.  They are looked up with .get(), never written
 # into the user's dict, so a reference config round-trips unchanged.
 #   RNG    'device' : Philox4x32-10 noise generated inside the CUDA kernel (default)
+#          'device-fast' : opt-in cheaper device stream (Philox4x32-7, 40 random bits per complex
+#                     sample); statistically equivalent, different realisations
 #          'numpy'  : noise drawn on the host from funcs._R in the reference's order
 #                     (bit-compatible stream; results match the reference to fp32 accuracy)
 #   DEVICE torch device string; default = current CUDA device

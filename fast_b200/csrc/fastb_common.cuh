@@ -38,11 +38,13 @@ constexpr uint32_t kStreamNoise = 0x5CE7E000u;
 constexpr uint32_t kStreamChi = 0x10CA3900u;
 constexpr uint32_t kStreamSubharm = 0x5AB4A200u;
 
-// Philox4x32-10 (Salmon et al. SC'11).  Key schedule is uniform across the warp.
-__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                               uint32_t k0, uint32_t k1) {
+// Philox4x32-R (Salmon et al. SC'11; R = 10 is the standard generator, R = 7 the smallest round
+// count Random123 documents as passing BigCrush).  Key schedule is uniform across the warp.
+template <int R>
+__device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                            uint32_t k0, uint32_t k1) {
 #pragma unroll
-    for (int i = 0; i < 10; ++i) {
+    for (int i = 0; i < R; ++i) {
         const uint32_t hi0 = __umulhi(kPhiloxM0, c0), lo0 = kPhiloxM0 * c0;
         const uint32_t hi1 = __umulhi(kPhiloxM1, c2), lo1 = kPhiloxM1 * c2;
         c0 = hi1 ^ c1 ^ k0;
@@ -53,6 +55,10 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
         k1 += kPhiloxW1;
     }
     return make_uint4(c0, c1, c2, c3);
+}
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                               uint32_t k0, uint32_t k1) {
+    return philox4x32<10>(c0, c1, c2, c3, k0, k1);
 }
 
 // log2 of a normal (non-denormal) float as the bare MUFU.LG2: __log2f wraps the same instruction in
@@ -124,6 +130,34 @@ __device__ __forceinline__ void noise_block_fields(uint32_t block, unsigned long
         ma[2 * G] = b >> 9;
         mr[2 * G + 1] = c >> 9;
         ma[2 * G + 1] = ((a & 0x1FFu) << 14) | ((b & 0x1FFu) << 5) | ((c >> 4) & 0x1Fu);
+    }
+}
+
+// ---- 'device-fast' phase-noise stream (opt-in, RNG='device-fast') ----------------------------
+// Same block / cell mapping, fed by FIVE Philox4x32-7 calls q < 5 with counter
+// (b, g lo, g hi, kStreamNoiseFast + q): 20 words W[4q + j].  Cell m < 16 owns word W[m] and byte
+// m % 4 of the extra word X = W[16 + m / 4]  (40 bits per complex sample instead of 46):
+//   radius field = W[m] & 0x7FFFFF                                        (23 bits)
+//   angle  field = ((W[m] >> 9) & 0x7FC000) ^ (byte << 8)                  (bits 22..8: 15 bits)
+// 35 Philox rounds per 16 samples instead of 60.
+constexpr uint32_t kStreamNoiseFast = 0x5CE7F000u;
+__device__ __forceinline__ void noise_block_fields_fast(uint32_t block, unsigned long long g, uint32_t k0,
+                                                        uint32_t k1, uint32_t (&mr)[16], uint32_t (&ma)[16]) {
+    uint32_t W[20];
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+        const uint4 w = philox4x32<7>(block, (uint32_t)g, (uint32_t)(g >> 32), kStreamNoiseFast + q, k0, k1);
+        W[4 * q] = w.x;
+        W[4 * q + 1] = w.y;
+        W[4 * q + 2] = w.z;
+        W[4 * q + 3] = w.w;
+    }
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+        const uint32_t w = W[m];
+        mr[m] = w & 0x7FFFFFu;
+        // byte m % 4 of the extra word moved to bits 15..8 (one PRMT), xor-ed under the word's top 9 bits
+        ma[m] = ((w >> 9) & 0x7FC000u) ^ __byte_perm(W[16 + m / 4], 0u, 0x4404u | ((m % 4) << 4));
     }
 }
 

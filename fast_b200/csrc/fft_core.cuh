@@ -297,6 +297,8 @@ struct LineFFT {
     static constexpr int kPlane = (kBufA > kBufC) ? kBufA : kBufC;   // float2 per plane
     static constexpr int kBuf = kPlane * Smem<V>::kPlanes;           // float2 per line (pair)
     static_assert(LOG2N >= 6 && LOG2N <= 11, "N must be 64..2048");
+    // the last stage can run on warp shuffles (phase_c_shfl): one line per group, 2 or 4 lanes per DFT
+    static constexpr bool kShflC = kThree && (S2 == 2 || S2 == 4) && TwOf<V>::kLines == 1;
 
     // element index held in register m of thread t before phase A
     FASTB_HD static int n_in(int t, int m) { return t + S1 * m; }
@@ -374,6 +376,79 @@ struct LineFFT {
         }
     }
 
+#if defined(__CUDACC__)
+    // Phase C through warp shuffles (S2 = 2 or 4, one line per thread group, device only): the S2
+    // threads u, u^1 (, u^2, u^3) of a group are adjacent lanes, so the S2 x S2 transposes of the
+    // last stage need no shared memory and no line barrier.  Thread j = u % S2 ends with
+    //   v[i S2 + b2] = sum_t2 x_t2[i S2 + j] w_S2^(t2 b2)      (x_t2 = phase-B register file of lane t2)
+    // exactly as phase_c leaves it.  KEEP (bit e = register e is consumed) prunes whole exchanges.
+    template <unsigned KEEP>
+    __device__ __forceinline__ static void phase_c_shfl(int u, float2 (&v)[16]) {
+        static_assert(kThree && (S2 == 2 || S2 == 4), "shuffle stage serves N = 512 and 1024");
+        constexpr unsigned kAll = 0xffffffffu;
+        auto xchg = [](float2 s, int lane_xor) {
+            return make_float2(__shfl_xor_sync(kAll, s.x, lane_xor), __shfl_xor_sync(kAll, s.y, lane_xor));
+        };
+        auto sel = [](bool c, float2 a, float2 b) { return make_float2(c ? a.x : b.x, c ? a.y : b.y); };
+        const bool b0 = u & 1;
+        const float s0 = b0 ? -1.f : 1.f;
+        if (S2 == 2) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const bool want_sum = (KEEP >> (2 * i)) & 1u, want_dif = (KEEP >> (2 * i + 1)) & 1u;
+                if (!want_sum && !want_dif) continue;
+                const float2 own = sel(b0, v[2 * i + 1], v[2 * i]);
+                const float2 got = xchg(sel(b0, v[2 * i], v[2 * i + 1]), 1);
+                if (want_sum) v[2 * i] = add2(own, got);
+                if (want_dif) v[2 * i + 1] = mul2(sub2(own, got), bc2(s0));    // x_0 - x_1
+            }
+        } else {
+            const bool b1 = u & 2;
+            const float s1 = b1 ? -1.f : 1.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const unsigned k4 = (KEEP >> (4 * i)) & 15u;
+                if (k4 == 0) continue;
+                const bool even = k4 & 5u, odd = k4 & 10u;
+                // step 1 (lane ^ 2): keep the two a2 whose owner shares my bit 1, trade the others
+                const float2 kA = sel(b1, v[4 * i + 2], v[4 * i]), kB = sel(b1, v[4 * i + 3], v[4 * i + 1]);
+                const float2 gA = xchg(sel(b1, v[4 * i], v[4 * i + 2]), 2);
+                const float2 gB = xchg(sel(b1, v[4 * i + 1], v[4 * i + 3]), 2);
+                // radix-2 over the t2 pair {t, t + 2}, t = u & 1: sums feed even b2, differences odd b2
+                float2 y0 = make_float2(0.f, 0.f), y1 = y0, y2 = y0, y3 = y0;
+                if (even) {
+                    const float2 SA = add2(kA, gA), SB = add2(kB, gB);
+                    const float2 mine = sel(b0, SB, SA), got = xchg(sel(b0, SA, SB), 1);   // lane ^ 1
+                    y0 = add2(mine, got);
+                    y2 = mul2(sub2(mine, got), bc2(s0));
+                }
+                if (odd) {
+                    const float2 DA = mul2(sub2(kA, gA), bc2(s1)), DB = mul2(sub2(kB, gB), bc2(s1));
+                    const float2 mine = sel(b0, DB, DA), got = xchg(sel(b0, DA, DB), 1);
+                    const float2 lo = sel(b0, got, mine), hi = sel(b0, mine, got);       // t = 0, t = 1
+                    y1 = caddi(lo, hi);
+                    y3 = csubi(lo, hi);
+                }
+                if (k4 & 1u) v[4 * i] = y0;
+                if (k4 & 2u) v[4 * i + 1] = y1;
+                if (k4 & 4u) v[4 * i + 2] = y2;
+                if (k4 & 8u) v[4 * i + 3] = y3;
+            }
+        }
+    }
+
+    // the whole line FFT with the shuffle last stage: two line syncs instead of four
+    template <unsigned KEEP, typename Sync>
+    __device__ __forceinline__ static void run_shfl(int u, float2 (&v)[16], const Tw* twa, const Tw* twb,
+                                                    float2* buf, Sync sync) {
+        phase_a(u, v, twa, buf);
+        sync();
+        phase_b(u, v, twb, buf);
+        sync();                 // every gather is done: the next line may overwrite the buffer
+        phase_c_shfl<KEEP>(u, v);
+    }
+#endif
+
     // the whole line FFT; `sync` synchronises the S1 threads of the line (pair)
     template <typename Sync>
     FASTB_HD static void run(int u, V (&v)[16], const Tw* twa, const Tw* twb, float2* buf, Sync sync) {
@@ -446,6 +521,9 @@ struct LineFFT32 {
     static constexpr int kTwRow = 34;
     static constexpr int kTwA = kTwRow * S1;
     static constexpr int kTwB = 0;
+    static constexpr bool kShflC = false;
+    template <unsigned KEEP, typename Sync>
+    FASTB_HD static void run_shfl(int, float2 (&)[32], const float2*, const float2*, float2*, Sync) {}
     FASTB_HD static int n_in(int t, int m) { return t + S1 * m; }
     FASTB_HD static int twa_exponent(int idx) {
         const int t = idx / kTwRow, a = idx % kTwRow;

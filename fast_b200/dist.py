@@ -51,16 +51,70 @@ def assemble(a, b, nchunks, ppc):
     return torch.stack([a.reshape(nchunks, ppc), b.reshape(nchunks, ppc)], dim=1).reshape(-1)
 
 
+class StatsBuffers:
+    """Moments / extrema / dB histogram of `n_items` result sets in ONE contiguous buffer of 8-byte
+    words, so that combining ranks is a single small collective:
+        [ sums: n_items x 8 f64 | minmax: n_items x 2 f64 | hist: n_items x (nbins + 2) i64 ]
+    The views `sums`, `minmax`, `hist` are what fastb_stats / the fused K2 epilogue accumulate into."""
+
+    def __init__(self, nbins, device, n_items=1, db_lo=-60.0, db_hi=3.0):
+        self.nbins, self.n_items, self.db_lo, self.db_hi = int(nbins), int(n_items), float(db_lo), float(db_hi)
+        a, b = self.n_items * 8, self.n_items * 10
+        words = b + self.n_items * (self.nbins + 2)
+        self.raw = torch.zeros(words, dtype=torch.int64, device=device)
+        self.sums = self.raw[:a].view(torch.float64).view(self.n_items, 8)
+        self.minmax = self.raw[a:b].view(torch.float64).view(self.n_items, 2)
+        self.hist = self.raw[b:].view(self.n_items, self.nbins + 2)
+        self.minmax[:, 0] = float('inf')
+        self.minmax[:, 1] = float('-inf')
+        self._init = self.raw.clone()
+        self._gathered = None
+
+    def reset(self):
+        self.raw.copy_(self._init)                 # one copy kernel
+
+    def allreduce(self):
+        """Combine the ranks in place with ONE collective: all-gather of the raw buffer (33 KB at
+        4096 bins) followed by a local reduction -- SUM for moments and histogram, MIN / MAX for the
+        extrema.  Latency-bound over NVLink; no-op on a single rank."""
+        _, world = rank_world()
+        if world == 1:
+            return self
+        if self._gathered is None or self._gathered.shape[0] != world:
+            self._gathered = torch.empty((world, self.raw.numel()), dtype=torch.int64, device=self.raw.device)
+        td.all_gather_into_tensor(self._gathered.view(-1), self.raw)
+        a, b = self.n_items * 8, self.n_items * 10
+        g = self._gathered
+        self.sums.copy_(g[:, :a].view(torch.float64).sum(0).view(self.n_items, 8))
+        mm = g[:, a:b].view(torch.float64).view(world, self.n_items, 2)
+        self.minmax[:, 0] = mm[:, :, 0].min(0).values
+        self.minmax[:, 1] = mm[:, :, 1].max(0).values
+        self.hist.copy_(g[:, b:].sum(0).view(self.n_items, self.nbins + 2))
+        return self
+
+    def summary(self, item=0):
+        return summarise(self.sums[item], self.minmax[item], self.hist[item], self.db_lo, self.db_hi)
+
+
+def broadcast_seed(seed, device):
+    """Rank 0's 64-bit seed on every rank (identity without torch.distributed)."""
+    _, world = rank_world()
+    if world == 1:
+        return int(seed)
+    dev = device if td.get_backend() == 'nccl' else 'cpu'
+    t = torch.tensor([int(seed) - (1 << 64) if int(seed) >= (1 << 63) else int(seed)], dtype=torch.int64, device=dev)
+    td.broadcast(t, src=0)
+    return int(t.item()) & 0xFFFFFFFFFFFFFFFF
+
+
 def new_stats_buffers(nbins, device):
-    sums = torch.zeros(8, dtype=torch.float64, device=device)
-    minmax = torch.tensor([float('inf'), float('-inf')], dtype=torch.float64, device=device)
-    hist = torch.zeros(nbins + 2, dtype=torch.int64, device=device)
-    return sums, minmax, hist
+    sb = StatsBuffers(nbins, device)
+    return sb.sums[0], sb.minmax[0], sb.hist[0]
 
 
 def allreduce_stats(sums, minmax, hist):
-    """Combine per-rank partial statistics in place: SUM for moments and histogram, MIN/MAX
-    for the extrema.  ~33 KB at 4096 bins: latency-bound over NVLink."""
+    """Combine separately allocated per-rank statistics in place (legacy three-buffer form; the
+    bench and Fast use StatsBuffers.allreduce, which needs one collective instead of four)."""
     _, world = rank_world()
     if world > 1:
         td.all_reduce(sums, op=td.ReduceOp.SUM)
@@ -91,8 +145,8 @@ def reduced_stats(r_local, db_lo=-60.0, db_hi=3.0, nbins=4096, already_global=Fa
     """fastb_stats on this rank's results, then the all-reduce (skipped when every rank
     already holds the full array)."""
     from . import _lib
-    sums, minmax, hist = new_stats_buffers(nbins, r_local.device)
-    _lib.stats(r_local.contiguous(), db_lo, db_hi, nbins, sums, minmax, hist)
+    sb = StatsBuffers(nbins, r_local.device, db_lo=db_lo, db_hi=db_hi)
+    _lib.stats(r_local.contiguous(), db_lo, db_hi, nbins, sb.sums[0], sb.minmax[0], sb.hist[0])
     if not already_global:
-        allreduce_stats(sums, minmax, hist)
-    return summarise(sums, minmax, hist, db_lo, db_hi)
+        sb.allreduce()
+    return sb.summary()

@@ -13,6 +13,7 @@ What runs where
                                  result statistics (fastb_stats)
 There is no CPU fallback for the device part.
 """
+import functools
 import logging
 import math
 
@@ -29,6 +30,18 @@ from . import temporal
 logger = logging.getLogger(__name__)
 
 _AO_MODES = {'NOAO': _lib.AO_NOAO, 'AO': _lib.AO_AO, 'TT': _lib.AO_AO, 'LGSAO': _lib.AO_LGSAO}
+_RNG_MODES = ('device', 'device-fast', 'numpy')
+_GOLDEN64 = 0x9E3779B97F4A7C15
+
+
+def _on_device(method):
+    """Run a method with the simulation's CUDA device current: the library launches on the current
+    device and stream, so a Fast built for 'cuda:1' must not depend on what the caller left current."""
+    @functools.wraps(method)
+    def wrapped(self, *args, **kwargs):
+        with torch.cuda.device(self.device):
+            return method(self, *args, **kwargs)
+    return wrapped
 
 
 class SpatialFrequencyStruct():
@@ -127,8 +140,8 @@ class Fast():
         self.temporal = self.params['TEMPORAL']
         self.dt = self.params['DT']
         self.rng_mode = self.params.get('RNG', conf.EXTRA_DEFAULTS['RNG'])
-        if self.rng_mode not in ('device', 'numpy'):
-            raise Exception("RNG must be 'device' or 'numpy'")
+        if self.rng_mode not in _RNG_MODES:
+            raise Exception("RNG must be 'device', 'device-fast' or 'numpy'")
 
         if self.Niter % self.Nchunks != 0:
             raise Exception('NCHUNKS must divide NITER without remainder')
@@ -140,16 +153,20 @@ class Fast():
         self.device = torch.device(dev) if dev is not None else torch.device('cuda', torch.cuda.current_device())
         self._d = {}                           # device tensors by name
         self._host_cache = {}
+        self._runs = 0                         # run() calls so far; _run_index = the current / last one
+        self._run_index = 0
+        self._prep_key = None
 
-        self.init_logging()
-        self.init_atmos()
-        self.init_beam_params()
-        self.init_frequency_grid()
-        self.init_ao_params()
-        self.init_pupil_mask()
-        self.init_phs_logamp()
-        self.compute_link_budget()
-        self.compute_powerspec()
+        with torch.cuda.device(self.device):
+            self.init_logging()
+            self.init_atmos()
+            self.init_beam_params()
+            self.init_frequency_grid()
+            self.init_ao_params()
+            self.init_pupil_mask()
+            self.init_phs_logamp()
+            self.compute_link_budget()
+            self.compute_powerspec()
         self.fftw_objs = None
 
     # ------------------------------------------------------------------ init (host scalars)
@@ -388,6 +405,7 @@ class Fast():
             pp.vx[i], pp.vy[i] = float(self.wind_vector[i, 0]), float(self.wind_vector[i, 1])
         return pp
 
+    @_on_device
     def compute_powerspec(self):
         """Residual phase PSD, log-amplitude PSD and the error-budget integrals
         (fast/fast.py:445-492) -- one fused kernel + one batched Simpson reduction."""
@@ -413,6 +431,7 @@ class Fast():
             d['weight_per_layer'] = torch.empty((L, N, N), dtype=torch.float32, device=dev)
             outs['weight_per_layer'] = d['weight_per_layer']
         _lib.psd_build(self._psd_params(), outs, lf_mask=lf, zfilter=zf, pupil_filter=d['pupil_filter'])
+        self._prep_key = None
         d['noise'], d['powerspec'], d['logamp'], d['powerspec_per_layer'] = slab[3], slab[4], slab[5], slab[6:]
         w = torch.from_numpy(funcs.simpson_weights(self.freq.main.f)).to(dev)
         ints = _lib.simpson2d(slab, w).cpu().numpy()
@@ -501,6 +520,7 @@ class Fast():
         rp.n, rp.n_pup, rp.lo = self.Npxls, self.Npxls_pup, self._lo
         rp.coherent = 1 if self.params['COHERENT'] else 0
         rp.algo = algo
+        rp.flags = _lib.RUN_RNG_FAST if self.rng_mode == 'device-fast' else 0
         rp.n_pairs, rp.first_pair = int(n_pairs), int(first_pair)
         rp.pairs_per_chunk = self.Niter_per_chunk // 2
         rp.seed = self._run_seed()
@@ -509,45 +529,82 @@ class Fast():
         return rp
 
     def _run_seed(self):
-        if self.seed != None:  # noqa: E711
-            return int(self.seed) & 0xFFFFFFFFFFFFFFFF
-        return self._auto_seed()
+        """Philox key of the current (or last) run.  Run k > 0 of one object uses the key
+        seed + k * 0x9E3779B97F4A7C15 (mod 2^64), so that successive run() calls draw fresh,
+        independent realisations like the reference's persistent generator does (fast/funcs.py:21),
+        while a new object with the same SEED reproduces the first run."""
+        base = int(self.seed) if self.seed != None else self._auto_seed()  # noqa: E711
+        return (base + self._run_index * _GOLDEN64) & 0xFFFFFFFFFFFFFFFF
 
     def _auto_seed(self):
         if not hasattr(self, '_seed_drawn'):
-            self._seed_drawn = int(numpy.random.SeedSequence().generate_state(2, numpy.uint32).view(numpy.uint64)[0])
+            drawn = int(numpy.random.SeedSequence().generate_state(2, numpy.uint32).view(numpy.uint64)[0])
+            # unseeded runs under torch.distributed: every rank uses rank 0's draw, so that the
+            # sharded result does not depend on the number of ranks
+            self._seed_drawn = dist.broadcast_seed(drawn, self.device)
         return self._seed_drawn
 
-    def _workspace(self, rp):
-        nbytes = _lib.screen_detect_workspace_bytes(rp)
+    def _workspace(self, rp, n_items=1):
+        nbytes = _lib.screen_detect_workspace_bytes(rp, n_items)
         ws = self._d.get('workspace')
         if ws is None or ws.numel() < nbytes:
             ws = self._d['workspace'] = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self._prep_key = None
         return ws
 
-    def screen_detect(self, first_pair, n_pairs, noise=None, chi=None, algo=_lib.ALGO_AUTO, noise_lo=None):
+    def _prepared_workspace(self, rp):
+        """Workspace whose derived tables (transposed U, pre-scaled weight copy / chirp tables) match
+        the current weight and U: prepared once, re-prepared when either tensor was written to."""
+        ws = self._workspace(rp)
+        w, U = self._d['weight'], self._d['U']
+        key = (ws.data_ptr(), w.data_ptr(), w._version, U.data_ptr(), U._version, int(rp.algo))
+        if self._prep_key != key:
+            _lib.screen_detect_prepare(rp, w, U, ws)
+            self._prep_key = key
+        return ws
+
+    @_on_device
+    def screen_detect(self, first_pair, n_pairs, noise=None, chi=None, algo=_lib.ALGO_AUTO, noise_lo=None,
+                      stats=None):
         """Run K2 for global pairs [first_pair, first_pair + n_pairs).  Returns two device
         tensors (results of the Re and Im realisations); complex64 when COHERENT.
         noise: optional (n_pairs, N, N) complex64 device tensor; chi: optional float32 device
-        tensor indexed by global realisation index."""
+        tensor indexed by global realisation index; stats: optional dist.StatsBuffers that the
+        kernel accumulates the moments / extrema / dB histogram of these results into."""
         rp = self._run_params(n_pairs, first_pair, algo)
         width = 2 if rp.coherent else 1
         out_a = torch.empty(n_pairs * width, dtype=torch.float32, device=self.device)
         out_b = torch.empty(n_pairs * width, dtype=torch.float32, device=self.device)
         if n_pairs:
-            nz = None if noise is None else torch.view_as_real(noise.contiguous())
-            sh = None
-            if self.subharmonics:
-                sh = dict(self._d['subharm'])
-                if noise_lo is not None:
-                    sh['noise'] = torch.view_as_real(noise_lo.contiguous())
-            _lib.screen_detect(rp, self._d['weight'], self._d['U'], out_a, out_b, self._workspace(rp),
-                               chi=chi, noise=nz, subharm=sh)
+            fused = noise is None and not self.subharmonics and algo != _lib.ALGO_RADIX_PAIR
+            if fused:
+                # device RNG: one launch -- tables prepared once per (weight, U), statistics fused
+                ws = self._prepared_workspace(rp)
+                rp.flags |= _lib.RUN_PREPARED
+                st = None if stats is None else _lib.run_stats(stats.db_lo, stats.db_hi, stats.nbins,
+                                                               stats.sums, stats.minmax, stats.hist)
+                _lib.screen_detect_batch(rp, self._d['weight'], self._d['U'], out_a, out_b, ws, stats=st, chi=chi)
+            else:
+                nz = None if noise is None else torch.view_as_real(noise.contiguous())
+                sh = None
+                if self.subharmonics:
+                    sh = dict(self._d['subharm'])
+                    if noise_lo is not None:
+                        sh['noise'] = torch.view_as_real(noise_lo.contiguous())
+                self._prep_key = None
+                _lib.screen_detect(rp, self._d['weight'], self._d['U'], out_a, out_b, self._workspace(rp),
+                                   chi=chi, noise=nz, subharm=sh)
         if rp.coherent:
             out_a = torch.view_as_complex(out_a.view(-1, 2))
             out_b = torch.view_as_complex(out_b.view(-1, 2))
+        if stats is not None and n_pairs and not fused:
+            r = torch.cat([out_a, out_b])
+            r = (r.real ** 2 + r.imag ** 2) if r.is_complex() else r
+            _lib.stats(r.contiguous(), stats.db_lo, stats.db_hi, stats.nbins, stats.sums[0], stats.minmax[0],
+                       stats.hist[0])
         return out_a, out_b
 
+    @_on_device
     def screens(self, first_pair, n_pairs, noise=None, noise_lo=None):
         """The cropped phase screens of global pairs [first_pair, first_pair + n_pairs) as a
         (2 n_pairs, Npup, Npup) float32 device tensor ordered [Re_0, Im_0, Re_1, Im_1, ...]
@@ -562,6 +619,7 @@ class Fast():
                 sh = dict(self._d['subharm'])
                 if noise_lo is not None:
                     sh['noise'] = torch.view_as_real(noise_lo.contiguous())
+            self._prep_key = None                  # the direct kernel's scratch overlaps the tables
             _lib.screens_crop(rp, self._d['weight'], phs, self._workspace(rp), noise=nz, subharm=sh)
         return phs
 
@@ -573,7 +631,7 @@ class Fast():
             # temporally coloured chi: Niter complex draws + one 1-D FFT on the host
             # (fast/funcs.py:367-375).  RNG='device' uses a generator derived from the seed.
             keep = funcs._R
-            if self.rng_mode == 'device':
+            if self.rng_mode != 'numpy':
                 funcs._R = numpy.random.default_rng([self._run_seed(), 0xC41])
             try:
                 self.logamp[:] = funcs.generate_random_coefficients_logamp(
@@ -648,9 +706,13 @@ class Fast():
         self.random_iters = torch.cat([a, b])
         return self.random_iters
 
+    @_on_device
     def run(self):
-        """Monte-Carlo run (fast/fast.py:115-140).  With torch.distributed initialised and
-        RNG='device', pair ranges are sharded over the ranks and gathered (fast_b200/dist.py)."""
+        """Monte-Carlo run (fast/fast.py:115-140).  With torch.distributed initialised and the
+        device RNG, pair ranges are sharded over the ranks and gathered (fast_b200/dist.py).
+        Successive calls give fresh realisations (see _run_seed)."""
+        self._run_index = self._runs
+        self._runs += 1
         logger.debug("Compute log amplitude values")
         self.compute_logamp()
         ppc = self.Niter_per_chunk // 2
@@ -661,7 +723,7 @@ class Fast():
                 self.compute_phs_temporal(chunk=i)
                 parts.append(self.compute_detector(chunk=i))
             flat = torch.cat(parts)
-        elif self.rng_mode == 'device':
+        elif self.rng_mode != 'numpy':
             rank, world = dist.rank_world()
             lo, hi = dist.shard_range(total, rank, world)
             a, b = self.screen_detect(lo, hi - lo)
@@ -677,13 +739,27 @@ class Fast():
             flat = torch.cat(parts)
             self._d.pop('noise', None)
         self._d['result'] = flat
-        I = flat.cpu().numpy()
-        I = I.astype(complex) if self.params['COHERENT'] else I.astype(float)
-        self.result = FastResult(I, self.diffraction_limit)
+        self.result = FastResult(self._to_host(flat), self.diffraction_limit)
         self.I = self.result.power
         logger.info(self.result)
         return self.result
 
+    def _to_host(self, flat):
+        """Device results -> the reference's host array (float64, complex128 when COHERENT) through a
+        pinned staging buffer that is reused across runs."""
+        src = torch.view_as_real(flat).reshape(-1) if flat.is_complex() else flat.reshape(-1)
+        n = src.numel()
+        buf = getattr(self, '_host_buf', None)
+        if buf is None or buf.numel() < n:
+            buf = self._host_buf = torch.empty(n, dtype=torch.float32, pin_memory=True)
+        buf[:n].copy_(src, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        host = buf[:n].numpy()
+        if flat.is_complex():
+            return host.view(numpy.complex64).astype(complex)
+        return host.astype(float)
+
+    @_on_device
     def result_stats(self, db_lo=-60.0, db_hi=3.0, nbins=4096):
         """Moments / extrema / dB histogram of the last run computed on the device
         (fastb_stats) and, under torch.distributed, all-reduced over the ranks' shards."""

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define FASTB_VERSION 100          /* major*10000 + minor*100 + patch */
+#define FASTB_VERSION 200          /* major*10000 + minor*100 + patch */
 #define FASTB_MAX_LAYERS 32
 
 enum {
@@ -160,6 +160,11 @@ int64_t fastb_pupil_filter_workspace_bytes(int32_t n);
  *   cell m = 2G+1: radius field W[3G+2] >> 9, angle field (W[3G]&511)<<14 | (W[3G+1]&511)<<5 | (W[3G+2]>>4)&31
  *   radius = sqrt(-2 ln(1 - field 2^-23)),  angle = 2 pi field 2^-23,
  *   Re = radius cos(angle), Im = radius sin(angle).
+ * 'device-fast' stream (FASTB_RUN_RNG_FAST): same block / cell mapping, five Philox4x32-7 calls
+ * q < 5 with counter (b, g lo, g hi, 0x5CE7F000 + q): 20 words W[4q+j].  Cell m < 16 owns word W[m]
+ * and byte m % 4 of the extra word W[16 + m/4]:
+ *   radius field = W[m] & 0x7FFFFF,   angle field = ((W[m] >> 9) & 0x7FC000) ^ (byte << 8)
+ * (40 random bits per complex sample, angle on a 2^-15 turn lattice), same Box-Muller.
  * chi_i = sigma_chi * n_i, n_i = normal (i % 4) of call i / 4 with counter
  * (i/4 lo, i/4 hi, 0, 0x10CA3900), Box-Muller on the top 23 bits of word pairs (0,1), (2,3).  Results depend only on (seed, g), never on the launch
  * geometry or the number of GPUs.
@@ -169,10 +174,21 @@ enum {
     FASTB_ALGO_DIRECT = 1,          /* pruned direct DFT, any even N */
     FASTB_ALGO_RADIX = 2,           /* register radix-16 FFT, one line per thread group, N = 64..2048
                                        power of two; what AUTO selects for those sizes */
-    FASTB_ALGO_RADIX_PAIR = 3       /* same FFT on two adjacent lines per thread group, all arithmetic
+    FASTB_ALGO_RADIX_PAIR = 3,      /* same FFT on two adjacent lines per thread group, all arithmetic
                                        in packed FP32 (FADD2/FMUL2/FFMA2): fewer instructions, but
                                        measured slower than RADIX on B200; kept as a cross-check */
+    FASTB_ALGO_BLUESTEIN = 4        /* any even N with N + n_pup - 1 <= 2048: chirp-z (Bluestein) on the
+                                       radix line FFT of length M = 2^ceil(log2(N + n_pup - 1)); what AUTO
+                                       selects for grids that are not a power of two (the reference's
+                                       NPXLS 'auto' sizes, fast/fast.py:166-187, e.g. 164) */
 };
+
+/* FastbRunParams.flags */
+#define FASTB_RUN_PREPARED 1        /* the workspace tables were filled by fastb_screen_detect_prepare for
+                                       the same (params, weight, U); skip the per-call preparation kernels */
+#define FASTB_RUN_RNG_FAST 2        /* opt-in 'device-fast' noise stream: Philox4x32-7, five calls per block
+                                       of 16 cells (see below); statistically equivalent, not bit-compatible
+                                       with the default stream */
 
 typedef struct FastbRunParams {
     int32_t n;                      /* N */
@@ -180,7 +196,7 @@ typedef struct FastbRunParams {
     int32_t lo;                     /* (N - n_pup) / 2 (fast/fast.py:390) */
     int32_t coherent;               /* 0: |z|^2 -> 1 float; 1: z -> 2 floats (re, im) */
     int32_t algo;                   /* FASTB_ALGO_* */
-    int32_t reserved;
+    int32_t flags;                  /* FASTB_RUN_* bits, 0 by default */
     int64_t n_pairs;                /* pairs in this call */
     int64_t first_pair;             /* global index g of the first pair */
     int64_t pairs_per_chunk;        /* NITER/NCHUNKS/2; > 0 */
@@ -223,6 +239,49 @@ int fastb_screen_detect(const FastbRunParams* p, const float* d_weight, const fl
                         float* d_out_a, float* d_out_b, void* d_workspace,
                         int64_t workspace_bytes, void* stream);
 
+/* ---- batched configurations and fused statistics ------------------------------------------------
+ * fastb_screen_detect_batch runs ONE launch over `n_items` configurations that share the grid, the
+ * crop and U but have their own weight table, sigma_chi and seed -- the elevation samples of a
+ * satellite pass that the reference builds one Fast object at a time
+ * (fast/complete_orbit_simulation.py:217-228).  Pairs are addressed by the flattened index
+ *   q = item * pairs_per_item + g,       g = pair index inside its configuration (RNG counter),
+ * FastbRunParams.first_pair / n_pairs select a range of q (so that (item x pair) ranges shard over
+ * GPUs), outputs are indexed by q - first_pair, and every item's values are bit-identical to a
+ * single-configuration run with that item's weight, sigma_chi and seed.  batch == NULL: a single
+ * configuration (d_weight one table, seed / sigma_chi from FastbRunParams).
+ *   d_weight   n_items * N*N floats
+ * Fused K3 (stats != NULL): moments, extrema and the dB histogram of the results of this launch are
+ * accumulated into per-item buffers while the scalars are written -- the same quantities, bin rule
+ * and accumulate-into semantics as fastb_stats, without a second pass:
+ *   d_sums [n_items][8], d_minmax [n_items][2], d_hist [n_items][nbins + 2].
+ * fastb_screen_detect_prepare fills the derived tables of the workspace (transposed U, pre-scaled
+ * interleaved weight copies or chirp tables); with FASTB_RUN_PREPARED set the run entry points skip
+ * their own preparation kernels, so a step is a single launch.  The tables depend on
+ * (n, n_pup, lo, algo, n_items, d_weight contents, d_U contents). */
+typedef struct FastbRunBatch {
+    int32_t n_items;                /* >= 1 */
+    int32_t reserved;
+    int64_t pairs_per_item;         /* NITER / 2 of each configuration */
+    const float* d_sigma_chi;       /* n_items floats */
+    const uint64_t* d_seeds;        /* n_items seeds */
+} FastbRunBatch;
+
+typedef struct FastbRunStats {
+    double db_lo, db_hi;            /* histogram range [db_lo, db_hi) in dB */
+    int32_t nbins, reserved;
+    double* d_sums;                 /* [n_items][8]  += { n, sum r, sum r^2, sum dB, sum dB^2, n(r <= 0), 0, 0 } */
+    double* d_minmax;               /* [n_items][2]   = { min(old, min r), max(old, max r) } */
+    unsigned long long* d_hist;     /* [n_items][nbins + 2], under/overflow in the last two */
+} FastbRunStats;
+
+int64_t fastb_screen_detect_batch_workspace_bytes(const FastbRunParams* p, int32_t n_items);
+int fastb_screen_detect_prepare(const FastbRunParams* p, int32_t n_items, const float* d_weight,
+                                const float* d_U, void* d_workspace, int64_t workspace_bytes, void* stream);
+int fastb_screen_detect_batch(const FastbRunParams* p, const FastbRunBatch* batch,
+                              const FastbRunStats* stats, const float* d_weight, const float* d_U,
+                              const float* d_chi, float* d_out_a, float* d_out_b, void* d_workspace,
+                              int64_t workspace_bytes, void* stream);
+
 /* Verification / inspection seam: the cropped phase screens themselves, as the reference keeps
  * them in `Fast.phs` (fast/fast.py:596, shape (J, n_pup, n_pup)).  Same inputs and numbering as
  * fastb_screen_detect; d_phs receives, for pair index p of this call, the Re screen at
@@ -236,6 +295,9 @@ int fastb_screens_crop(const FastbRunParams* p, const float* d_weight, const flo
  * and the chi normals of realisations [first, first+count).  Either output may be NULL. */
 int fastb_rng_dump(uint64_t seed, int64_t pair, int32_t n, float* d_noise_tile,
                    int64_t chi_first, int64_t chi_count, float* d_chi_normals, void* stream);
+/* same with the noise stream selected: rng_fast = 0 default stream, 1 'device-fast' */
+int fastb_rng_dump_mode(uint64_t seed, int64_t pair, int32_t n, int32_t rng_fast, float* d_noise_tile,
+                        int64_t chi_first, int64_t chi_count, float* d_chi_normals, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * K4: TEMPORAL (frozen-flow) mode -- Fast.compute_phs_temporal (fast/fast.py:607-637).

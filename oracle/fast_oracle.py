@@ -569,14 +569,18 @@ STREAM_NOISE = 0x5CE7E000      # counter word 3 tag: phase-noise cells
 STREAM_CHI = 0x10CA3900        # counter word 3 tag: log-amplitude draws
 
 
-def philox4x32_10(c0, c1, c2, c3, k0, k1):
-    """Vectorised Philox4x32-10.  Inputs broadcastable uint32 arrays; returns 4 uint32 arrays."""
+STREAM_NOISE_FAST = 0x5CE7F000  # counter word 3 tag: phase-noise cells of the 'device-fast' stream
+
+
+def philox4x32_10(c0, c1, c2, c3, k0, k1, rounds=10):
+    """Vectorised Philox4x32-R (R = 10 by default; the 'device-fast' stream uses R = 7).  Inputs
+    broadcastable uint32 arrays; returns 4 uint32 arrays."""
     c0, c1, c2, c3 = [np.asarray(x, dtype=np.uint64) for x in np.broadcast_arrays(c0, c1, c2, c3)]
     k0 = int(k0) & 0xFFFFFFFF
     k1 = int(k1) & 0xFFFFFFFF
     mask = np.uint64(0xFFFFFFFF)
     sh = np.uint64(32)
-    for _ in range(10):
+    for _ in range(rounds):
         p0 = PHILOX_M0 * c0
         p1 = PHILOX_M1 * c2
         hi0, lo0 = p0 >> sh, p0 & mask
@@ -611,12 +615,37 @@ def _bm_fields(mr, ma):
     return r * np.cos(t) + 1j * r * np.sin(t)
 
 
-def device_noise_pair(seed, pair, N):
+def device_noise_pair_fast(seed, pair, N):
+    """The 'device-fast' stream (include/fastb.h, FASTB_RUN_RNG_FAST): same block / cell mapping,
+    five Philox4x32-7 calls q with counter (b, pair lo, pair hi, STREAM_NOISE_FAST + q) give 20
+    words; cell m owns word W[m] and byte m % 4 of the extra word W[16 + m // 4]:
+    radius field = W[m] & 0x7FFFFF, angle field = ((W[m] >> 9) & 0x7FC000) ^ (byte << 8)."""
+    S = (N + 15) // 16
+    b = (np.arange(N, dtype=np.uint64)[:, None] * np.uint64(S) + np.arange(S, dtype=np.uint64)[None, :])
+    W = []
+    for q in range(5):
+        W.extend(philox4x32_10(b, np.uint64(pair & 0xFFFFFFFF), np.uint64((pair >> 32) & 0xFFFFFFFF),
+                               np.uint64(STREAM_NOISE_FAST + q), seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF,
+                               rounds=7))
+    out = np.zeros((N, S * 16), dtype=complex)
+    t = np.arange(S)
+    for m in range(16):
+        w = W[m]
+        byte = (W[16 + m // 4] >> np.uint32(8 * (m % 4))) & np.uint32(0xFF)
+        mr = w & np.uint32(0x7FFFFF)
+        ma = ((w >> np.uint32(9)) & np.uint32(0x7FC000)) ^ (byte << np.uint32(8))
+        out[:, t + S * m] = _bm_fields(mr, ma)
+    return out[:, :N]
+
+
+def device_noise_pair(seed, pair, N, fast=False):
     """The complex white-noise tile the CUDA generator produces for global pair index `pair`
     (contract: include/fastb.h).  Noise block b = r*S + t, S = ceil(N/16), holds cells
     (r, t + S m), m < 16; six Philox calls q with counter (b, pair lo, pair hi, STREAM_NOISE + q)
     give 24 words; each word triple feeds two Box-Muller pairs (top 23 bits of each word, plus
     one field mixed from the three low 9-bit remainders)."""
+    if fast:
+        return device_noise_pair_fast(seed, pair, N)
     S = (N + 15) // 16
     b = (np.arange(N, dtype=np.uint64)[:, None] * np.uint64(S) + np.arange(S, dtype=np.uint64)[None, :])
     W = []
@@ -648,7 +677,7 @@ def device_chi_normals(seed, first, count):
     return np.choose((idx & np.uint64(3)).astype(int), [n0, n1, n2, n3])
 
 
-def run_mc_device_rng(init, seed, n_pairs, pairs_per_chunk, coherent=None):
+def run_mc_device_rng(init, seed, n_pairs, pairs_per_chunk, coherent=None, fast=False, noise_of=None):
     """Oracle of the CUDA path in device-RNG mode for global pairs [0, n_pairs): same
     realisation layout as Fast.run() (chunk-major, Re-half then Im-half inside a chunk) with
     noise from device_noise_pair and chi from device_chi_normals."""
@@ -662,7 +691,9 @@ def run_mc_device_rng(init, seed, n_pairs, pairs_per_chunk, coherent=None):
         chunk, pp = divmod(g, pairs_per_chunk)
         i_re = chunk * 2 * pairs_per_chunk + pp
         i_im = i_re + pairs_per_chunk
-        noise = device_noise_pair(seed, g, N)[None]
+        # noise_of(g): the tile dumped from the device (fastb_rng_dump) instead of the restatement,
+        # which removes the ~1e-6 MUFU difference of the noise itself from the comparison
+        noise = (noise_of(g) if noise_of is not None else device_noise_pair(seed, g, N, fast))[None]
         phs = screens_from_noise(noise, init['powerspec'], init['df'], init['lo'], init['hi'])
         r = detector(phs, U, chi_all[[i_re, i_im]], coherent)
         out[i_re], out[i_im] = r[0], r[1]

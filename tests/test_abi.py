@@ -37,10 +37,29 @@ def test_struct_layout_matches_header(lib):
     assert ctypes.sizeof(lib.PsdParams) == 8 * 4 + 11 * 8 + 4 * 32 * 8
     assert ctypes.sizeof(lib.RunParams) == 6 * 4 + 3 * 8 + 8 + 8 + 4 + 4
     assert ctypes.sizeof(lib.PsdOutputs) == 10 * 8 and ctypes.sizeof(lib.PsdInputs) == 3 * 8
+    assert ctypes.sizeof(lib.RunBatch) == 2 * 4 + 8 + 2 * 8
+    assert ctypes.sizeof(lib.RunStats) == 2 * 8 + 2 * 4 + 3 * 8
+    assert lib.RunParams.flags.offset == 20 and lib.RunParams.n_pairs.offset == 24
+
+
+def test_run_argument_validation_without_gpu(lib):
+    """Validation happens before any CUDA call: bad flags, algorithms and batch geometry are
+    refused with a message, on a box without a GPU too."""
+    rp = lib.RunParams()
+    rp.n, rp.n_pup, rp.lo, rp.n_pairs, rp.pairs_per_chunk, rp.u_sum = 64, 8, 28, 1, 1, 1.0
+    rp.flags = 64
+    assert lib.lib.fastb_screen_detect_batch_workspace_bytes(ctypes.byref(rp), 1) == -1
+    assert b'flags' in lib.lib.fastb_last_error()
+    rp.flags, rp.algo = 0, lib.ALGO_BLUESTEIN + 1
+    assert lib.lib.fastb_screen_detect_batch_workspace_bytes(ctypes.byref(rp), 1) == -1
+    assert b'algo' in lib.lib.fastb_last_error()
+    rp.algo, rp.n, rp.n_pup, rp.lo = lib.ALGO_BLUESTEIN, 2000, 200, 900
+    assert lib.lib.fastb_screen_detect_batch_workspace_bytes(ctypes.byref(rp), 1) == -1
+    assert b'chirp-z' in lib.lib.fastb_last_error()
 
 
 def test_version_and_error_text(lib):
-    assert lib.version() == 100
+    assert lib.version() == 200
     rp = lib.RunParams()
     rp.n, rp.n_pup, rp.lo, rp.n_pairs, rp.pairs_per_chunk, rp.u_sum = 63, 8, 0, 1, 1, 1.0
     assert lib.lib.fastb_screen_detect_workspace_bytes(ctypes.byref(rp)) == -1

@@ -42,8 +42,18 @@ def _worker(rank, world, port, out):
         minmax[0], minmax[1] = float(g.min()), float(g.max())
         hist[rank] = 5
         dist.allreduce_stats(sums, minmax, hist)
+        # the packed form: 2 items, one collective
+        sb = dist.StatsBuffers(8, torch.device('cpu'), n_items=2)
+        sb.sums[0, 0], sb.sums[1, 1] = hi - lo, 10.0 * (rank + 1)
+        sb.minmax[0, 0], sb.minmax[0, 1] = float(g.min()), float(g.max())
+        sb.hist[1, rank] = 7
+        sb.allreduce()
+        packed = dict(sums=sb.sums.numpy().copy(), minmax=sb.minmax.numpy().copy(), hist=sb.hist.numpy().copy())
+        sb.reset()
+        packed['reset_ok'] = bool(sb.sums.abs().sum() == 0 and sb.hist.sum() == 0 and torch.isinf(sb.minmax).all())
+        seed = dist.broadcast_seed(0xFEDCBA9876543210 + rank, torch.device('cpu'))
         out[rank] = dict(flat=flat.numpy(), cflat=cflat.numpy(), sums=sums.numpy(), minmax=minmax.numpy(),
-                         hist=hist.numpy(), rw=dist.rank_world())
+                         hist=hist.numpy(), rw=dist.rank_world(), packed=packed, seed=seed)
     finally:
         td.destroy_process_group()
 
@@ -90,3 +100,26 @@ def test_world_size_2_gather_and_allreduce():
         assert o['sums'][0] == total and o['sums'][1] == g.sum()
         assert o['minmax'][0] == 0 and o['minmax'][1] == total - 1
         np.testing.assert_array_equal(o['hist'][:2], [5, 5])
+        pk = o['packed']
+        assert pk['sums'][0, 0] == total and pk['sums'][1, 1] == 30.0
+        assert pk['minmax'][0, 0] == 0 and pk['minmax'][0, 1] == total - 1
+        assert np.isinf(pk['minmax'][1]).all()
+        np.testing.assert_array_equal(pk['hist'][1, :2], [7, 7])
+        assert pk['hist'][0].sum() == 0 and pk['reset_ok']
+        assert o['seed'] == 0xFEDCBA9876543210          # rank 0's draw on every rank
+
+
+def test_flattened_item_pair_ranges_shard_like_a_batch():
+    """C3: the (sample x pair) range of a batched sweep is split contiguously over the ranks;
+    every flattened index maps to exactly one (item, pair) and items may straddle ranks."""
+    from fast_b200 import dist
+    E, ppi = 16, 5000
+    for world in (1, 2, 4, 8, 3):
+        seen = np.zeros(E * ppi, dtype=int)
+        for rank in range(world):
+            lo, hi = dist.shard_range(E * ppi, rank, world)
+            q = np.arange(lo, hi)
+            item, g = q // ppi, q % ppi
+            assert (item * ppi + g == q).all() and item.max(initial=0) < E
+            seen[lo:hi] += 1
+        assert (seen == 1).all()

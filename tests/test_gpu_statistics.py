@@ -18,12 +18,16 @@ from conftest import GOLDEN, load_golden
 pytestmark = pytest.mark.gpu
 
 
-def test_c2_db_rel_distribution_matches_reference():
+RNGS = ['device', 'device-fast']      # default stream and the opt-in Philox4x32-7 / 40-bit stream
+
+
+@pytest.mark.parametrize('rng', RNGS)
+def test_c2_db_rel_distribution_matches_reference(rng):
     import fast_b200
     ref = np.load(os.path.join(GOLDEN, 'c2_dist_1e5.npz'))['r'].astype(float)
     db_ref = 10 * np.log10(ref)
     _, p = load_golden('c2')
-    sim = fast_b200.Fast(dict(p, NITER=1000000, NCHUNKS=10, SEED=20261017))
+    sim = fast_b200.Fast(dict(p, NITER=1000000, NCHUNKS=10, SEED=20261017, RNG=rng))
     db = sim.run().dB_rel
     assert db.shape == (1000000,) and np.isfinite(db).all()
 
@@ -84,6 +88,29 @@ def _compare_db(db, db_ref, label):
     assert ks.pvalue > 0.01
 
 
+def test_fast_stream_agrees_with_the_default_stream_at_high_resolution():
+    """Device vs device at 2e6 realisations each (C2): the two generators must give the same dB_rel
+    distribution to a resolution ~4x finer than the comparison with the 1e5-sample reference allows."""
+    import fast_b200
+    _, p = load_golden('c2')
+    db = {}
+    for rng in RNGS:
+        sim = fast_b200.Fast(dict(p, NITER=2000000, NCHUNKS=10, SEED=424242, RNG=rng))
+        db[rng] = sim.run().dB_rel
+    a, b = db['device'], db['device-fast']
+    assert not np.array_equal(a, b)
+    se_mean = np.sqrt(a.var() / a.size + b.var() / b.size)
+    assert abs(a.mean() - b.mean()) < 4 * se_mean
+    assert abs(a.var() - b.var()) < 0.01 * a.var()
+    ks = stats.ks_2samp(a, b)
+    print(f'fast vs default: mean {a.mean():.4f} / {b.mean():.4f}, var {a.var():.4f} / {b.var():.4f}, KS p={ks.pvalue:.3f}')
+    assert ks.pvalue > 0.01
+    # deep-fade tail probabilities (what link budgets read off the distribution)
+    for thr in (-6.0, -10.0):
+        pa, pb = (a < thr).mean(), (b < thr).mean()
+        assert abs(pa - pb) < 4 * np.sqrt(pa * (1 - pa) * 2 / a.size) + 1e-6
+
+
 def _golden_dist(fname):
     path = os.path.join(GOLDEN, fname)
     if not os.path.exists(path):
@@ -91,21 +118,23 @@ def _golden_dist(fname):
     return np.load(path)['r']
 
 
-def test_c3_low_elevation_distribution_matches_reference():
+@pytest.mark.parametrize('rng', RNGS)
+def test_c3_low_elevation_distribution_matches_reference(rng):
     """C3 sample at 10 degrees elevation: strong turbulence, deep fades (mean about -14 dB)."""
     import fast_b200
     ref = _golden_dist('c3_el10_dist_5e4.npz').astype(float)
     _, p = load_golden('c3_el10')
-    sim = fast_b200.Fast(dict(p, NITER=500000, NCHUNKS=10, SEED=7))
+    sim = fast_b200.Fast(dict(p, NITER=500000, NCHUNKS=10, SEED=7, RNG=rng))
     _compare_db(sim.run().dB_rel, 10 * np.log10(ref), 'c3_el10')
 
 
-def test_c4_coherent_distribution_matches_reference():
+@pytest.mark.parametrize('rng', RNGS)
+def test_c4_coherent_distribution_matches_reference(rng):
     """C4 (512 x 512, coherent): modulus in dB and the phase of the complex field."""
     import fast_b200
     ref = _golden_dist('c4_dist_5e4.npz').astype(complex)
     _, p = load_golden('c4')
-    sim = fast_b200.Fast(dict(p, NITER=200000, NCHUNKS=10, SEED=8))
+    sim = fast_b200.Fast(dict(p, NITER=200000, NCHUNKS=10, SEED=8, RNG=rng))
     z = sim.run()._r
     assert z.dtype == complex
     _compare_db(20 * np.log10(np.abs(z)), 20 * np.log10(np.abs(ref)), 'c4 |z|^2')
@@ -114,10 +143,11 @@ def test_c4_coherent_distribution_matches_reference():
     assert ks.pvalue > 0.01
 
 
-def test_c5_large_grid_distribution_matches_reference():
+@pytest.mark.parametrize('rng', RNGS)
+def test_c5_large_grid_distribution_matches_reference(rng):
     """C5 (1024 x 1024): 1e5 device-RNG realisations vs 1e4 reference realisations."""
     import fast_b200
     ref = _golden_dist('c5_dist_1e4.npz').astype(float)
     _, p = load_golden('c5')
-    sim = fast_b200.Fast(dict(p, NITER=100000, NCHUNKS=10, SEED=9))
+    sim = fast_b200.Fast(dict(p, NITER=100000, NCHUNKS=10, SEED=9, RNG=rng))
     _compare_db(sim.run().dB_rel, 10 * np.log10(ref), 'c5')

@@ -131,6 +131,35 @@ def test_philox_known_answers():
         [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
 
 
+def test_philox_7_round_known_answers():
+    """Random123 known-answer vectors for philox4x32-7 (kat_vectors): the round function of the
+    opt-in 'device-fast' noise stream."""
+    def h(*a):
+        return [int(x) for x in fo.philox4x32_10(*a, rounds=7)]
+    assert h(0, 0, 0, 0, 0, 0) == [0x5f6fb709, 0x0d893f64, 0x4f121f81, 0x4f730a48]
+    f = 0xffffffff
+    assert h(f, f, f, f, f, f) == [0x5207ddc2, 0x45165e59, 0x4d8ee751, 0x8c52f662]
+    assert h(0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344, 0xa4093822, 0x299f31d0) == \
+        [0x4dfccaba, 0x190a87f0, 0xc47362ba, 0xb6b5242a]
+
+
+def test_fast_stream_noise_is_standard_normal_and_independent_of_the_default_stream():
+    z = fo.device_noise_pair(seed=7, pair=3, N=128, fast=True)
+    x = np.concatenate([z.real.ravel(), z.imag.ravel()])
+    assert abs(x.mean()) < 4 / np.sqrt(x.size)
+    assert abs(x.var() - 1) < 4 * np.sqrt(2 / x.size)
+    assert abs(np.mean(z.real * z.imag)) < 4 / np.sqrt(z.size)
+    # fourth moment of a standard normal is 3; lag-1 correlations along both axes vanish
+    assert abs(np.mean(x ** 4) - 3) < 4 * np.sqrt(96 / x.size)
+    assert abs(np.mean(z.real[:, 1:] * z.real[:, :-1])) < 4 / np.sqrt(z.size)
+    assert abs(np.mean(z.real[1:] * z.real[:-1])) < 4 / np.sqrt(z.size)
+    # angles lie on the 2^-15 turn lattice the contract states
+    turn = (np.angle(z) / (2 * np.pi)) % 1.0
+    assert np.abs(turn * 2 ** 15 - np.round(turn * 2 ** 15)).max() < 1e-6
+    z0 = fo.device_noise_pair(seed=7, pair=3, N=128)
+    assert abs(np.corrcoef(z.real.ravel(), z0.real.ravel())[0, 1]) < 4 / np.sqrt(z.size)
+
+
 def test_device_noise_is_standard_normal():
     z = fo.device_noise_pair(seed=7, pair=3, N=128)
     x = np.concatenate([z.real.ravel(), z.imag.ravel()])
