@@ -471,15 +471,19 @@ def per_workload(world, rank, flush, peak, dev):
     torch.cuda.synchronize()
     if world > 1:
         td.barrier()
-    flush.fill_(3)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    e0.record()
-    res = sweep.run_sweep(sims, stats=True)
-    e1.record()
-    e1.synchronize()
-    wall = time.perf_counter() - t0
-    ms = sync_max(e0.elapsed_time(e1))
+    runs = []
+    for rep in range(3):
+        flush.fill_(3 + rep)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        res = sweep.run_sweep(sims, stats=True)
+        e1.record()
+        e1.synchronize()
+        runs.append((sync_max(e0.elapsed_time(e1)), time.perf_counter() - t0))
+    runs.sort()
+    ms, wall = runs[1]
     if rank == 0:
         entry('c3_sweep', 160000, ms, 256, False, 'screen_detect_radix<N=256, window 2>, 16-item batch',
               note="device time of sweep.run_sweep: stack weights, ONE K2 launch over 16 x 5000 pairs, statistics "

@@ -13,8 +13,10 @@ import sys
 ROOT = os.path.dirname(os.path.abspath(__file__))
 HERE = os.path.join(ROOT, 'fast_b200')
 CSRC = os.path.join(HERE, 'csrc')
-LIB = os.path.join(HERE, 'libfastb.so')
-STAMP = os.path.join(HERE, 'build', 'libfastb.stamp')
+# tuning builds (FASTB_TUNE=1) go to their own library so that the product .so is never replaced by one
+TUNE = bool(os.environ.get('FASTB_TUNE'))
+LIB = os.path.join(HERE, 'libfastb_tune.so' if TUNE else 'libfastb.so')
+STAMP = os.path.join(HERE, 'build', 'libfastb_tune.stamp' if TUNE else 'libfastb.stamp')
 ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
 COMMON = ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']
 # per-file extra flags: the PSD kernel follows numpy's operation order (no FMA contraction)
@@ -59,7 +61,7 @@ def build(force=False, verbose=False):
     if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read() == dig:
         return LIB
     nvcc = os.environ.get('NVCC', 'nvcc')
-    objdir = os.path.join(HERE, 'build')
+    objdir = os.path.join(HERE, 'build', 'tune' if TUNE else 'product')
     os.makedirs(objdir, exist_ok=True)
     objs = []
     procs = []

@@ -10,7 +10,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libfastb.so')
+# FASTB_LIBRARY: tuning runs only (an alternative build of the same ABI, e.g. libfastb_tune.so)
+LIB_PATH = os.environ.get('FASTB_LIBRARY') or os.path.join(_HERE, 'libfastb.so')
 
 MAX_LAYERS = 32
 AO_NOAO, AO_AO, AO_LGSAO = 0, 1, 2

@@ -46,7 +46,7 @@ int launch_pair_n(int log2n, const RunArgs& a, const RadixRequest& rq, cudaStrea
     return FASTB_ERR_UNSUPPORTED;
 }
 
-int radix_ctas_per_sm(int log2n) { return log2n <= 8 ? 4 : (log2n == 9 ? 2 : 3); }
+int radix_ctas_per_sm(int log2n) { return log2n <= 8 ? 4 : 1; }
 
 // general even N through Bluestein's chirp-z on the radix line FFT (screen_detect_bluestein.cu)
 bool bluestein_ok(int n, int n_pup);
@@ -411,7 +411,12 @@ static int run_impl(const char* who, const FastbRunParams* p, const FastbRunBatc
     }
     if (p->n_pairs == 0) return FASTB_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    const int impl = pick_impl(p);
+    int impl = pick_impl(p);
+    if (impl == kImplBluestein && sh) {
+        // the sub-harmonic term is fused into the radix and direct kernels only
+        FASTB_REQUIRE(p->algo != FASTB_ALGO_BLUESTEIN, "%s: the chirp-z kernel has no sub-harmonic term", who);
+        impl = kImplDirect;
+    }
     const bool fast = (p->flags & FASTB_RUN_RNG_FAST) != 0;
     const int rng = d_noise ? kRngHost : (fast ? kRngFast : kRngPhilox);
     if (impl == kImplPair) {

@@ -370,7 +370,10 @@ struct LineSync {
 // Line-FFT flavour and CTA shape per grid size, measured on B200 (profiles/)
 //   N <= 256 : 128 threads x 4 CTAs/SM (128 registers) -- small CTAs keep the per-pair
 //              barriers cheap and balance the pupil columns over 8 lines per iteration
-//   N  = 512 : 256 threads x 2 CTAs/SM (125 registers); N >= 1024: 256 x 3 (80 registers)
+//   N >= 512 : 512 threads x 1 CTA/SM (128 registers): one scratch slot per SM keeps the pass-1 ->
+//              pass-2 intermediate of all SMs (148 x 8 n_pup N bytes) in or near the 126 MB L2
+//              (same-box A/B, profiles/experiments_r02.txt: +3.4 % at N = 512 over 256 x 2,
+//              +6.2 % at N = 1024 over 256 x 3)
 // All use the 16-elements-per-thread FFT.  A 32-elements-per-thread flavour (512 = 32 x 16,
 // 1024 = 32 x 32: one exchange per line, 168 registers) is kept for tuning builds: it measured the
 // same throughput in every CTA shape.
@@ -379,8 +382,8 @@ struct RadixCfg;
 template <int LOG2N>
 struct RadixCfg<LOG2N, 16> {
     using F = LineFFT<LOG2N>;
-    static constexpr int kThreadsPerCta = LOG2N <= 8 ? 128 : 256;
-    static constexpr int kMinBlocks = LOG2N <= 8 ? 4 : (LOG2N == 9 ? 2 : 3);
+    static constexpr int kThreadsPerCta = LOG2N <= 8 ? 128 : 512;
+    static constexpr int kMinBlocks = LOG2N <= 8 ? 4 : 1;
 };
 template <int LOG2N>
 struct RadixCfg<LOG2N, 32> {

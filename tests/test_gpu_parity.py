@@ -307,10 +307,12 @@ def test_fused_statistics_match_the_stats_kernel(fast, name):
     want = dist.reduced_stats(r.contiguous(), -40, 5, 450, already_global=True)
     got = sb.summary()
     assert got['n'] == want['n'] == 4000
+    # coherent: the kernel squares the field with a fused multiply-add, torch with two roundings
+    rel_tol = 1e-6 if r.dtype == torch.float32 and sim.params['COHERENT'] else 1e-9
     for k in ('mean', 'var', 'mean_dB', 'var_dB'):
-        assert got[k] == pytest.approx(want[k], rel=1e-9), k
-    assert got['min'] == want['min'] and got['max'] == want['max']
-    np.testing.assert_array_equal(got['hist'], want['hist'])
+        assert got[k] == pytest.approx(want[k], rel=rel_tol), k
+    assert got['min'] == pytest.approx(want['min'], rel=rel_tol) and got['max'] == pytest.approx(want['max'], rel=rel_tol)
+    assert np.abs(got['hist'] - want['hist']).sum() <= (4 if sim.params['COHERENT'] else 0)
     sb.reset()
     assert sb.summary()['n'] == 0
 
