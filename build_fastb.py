@@ -31,6 +31,7 @@ SOURCES = {
     'stats': ('stats.cu', []),
     'link_metrics': ('link_metrics.cu', ['-fmad=false']),
     'temporal': ('temporal.cu', []),
+    'layer_screens_fft': ('layer_screens_fft.cu', ['-Xptxas', '-v']),
 }
 for _k in range(6, 12):
     SOURCES[f'screen_detect_radix_{_k}'] = ('screen_detect_radix.cu', ['-Xptxas', '-v', f'-DFASTB_LOG2N={_k}'] + _DBG)

@@ -7,6 +7,7 @@
 namespace fastb {
 
 TuneHook g_tune_hook = nullptr;
+int g_l2_persist = 0;
 
 #define FASTB_DECL_SIZE(k)                                                                    \
     int launch_radix_##k(const RunArgs& a, const RadixRequest& rq, cudaStream_t st);         \

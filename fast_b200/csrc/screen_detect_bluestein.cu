@@ -10,6 +10,7 @@
 // Same pass structure, scratch layout, RNG contract and epilogue as the radix kernel
 // (screen_detect_kernel.cuh); replaces the O(N^2)-per-line direct kernel on the default path.
 #include "screen_detect_kernel.cuh"
+#include "bluestein.cuh"
 
 namespace fastb {
 namespace {
@@ -66,9 +67,6 @@ __global__ void __launch_bounds__(256) bluestein_tables_kernel(int N, int M, int
     }
 }
 
-__device__ __forceinline__ float2 cmulf(float2 a, float2 b) {
-    return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
-}
 
 template <int LOG2M, int RNG, int THREADS>
 __global__ void __launch_bounds__(THREADS, THREADS <= 128 ? 4 : 2) screen_detect_bluestein(const __grid_constant__ RunArgs a,
@@ -117,22 +115,7 @@ __global__ void __launch_bounds__(THREADS, THREADS <= 128 ? 4 : 2) screen_detect
 
     // chirp-z of the line held as v[m] = a[u + S1 m] (a = x c, zero beyond N): on return v[e] holds
     // sum_n a[n] conj(c[k - n]) for k = k_out(u, e), valid where `need` says so
-    auto convolve = [&](float2 (&v)[16]) {
-        F::run(u, v, twa, twb, buf, sync);
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-            const int k = F::k_base(u) + F::k_off(e);
-            const float2 z = cmulf(v[e], bhat[k]);
-            buf[k] = make_float2(z.x, -z.y);                  // conj(A B), natural order
-        }
-        sync();
-#pragma unroll
-        for (int m = 0; m < 16; ++m) v[m] = buf[u + S1 * m];
-        sync();
-        F::run(u, v, twa, twb, buf, sync);
-#pragma unroll
-        for (int e = 0; e < 16; ++e) v[e].y = -v[e].y;        // y = conj(G(.)); the 1/M sits in bhat
-    };
+    auto convolve = [&](float2 (&v)[16]) { chirp_convolve<F>(u, v, twa, twb, buf, bhat, sync); };
 
     for (long long pair = blockIdx.x; pair < a.n_pairs; pair += gridDim.x) {
         const PairId id = pair_id(a, pair);
@@ -260,6 +243,8 @@ int launch_blue(const RunArgs& a, const RadixRequest& rq, const float2* tables, 
 }
 
 }  // namespace
+
+int bluestein_log2m(int n, int n_pup) { return blue_log2m(n, n_pup); }
 
 bool bluestein_ok(int n, int n_pup) { return n >= 4 && (n % 2) == 0 && n + n_pup - 1 <= 2048; }
 

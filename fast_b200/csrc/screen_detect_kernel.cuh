@@ -84,6 +84,8 @@ int radix_ctas_per_sm(int log2n);     // design occupancy (scratch sizing)
 // returns < 0 when it does not handle the request
 typedef int (*TuneHook)(int log2n, const RunArgs& a, const RadixRequest& rq, cudaStream_t st);
 extern TuneHook g_tune_hook;
+// L2 residency hint for the scratch slots (launch_kernel): 0 off, 1 persisting access-policy window
+extern int g_l2_persist;
 
 namespace {
 
@@ -406,9 +408,13 @@ struct RadixCfg<LOG2N, 32> {
 template <int N>
 constexpr int window_half(int win) { return win == 1 ? N / 8 : win == 2 ? 3 * N / 16 : win == 3 ? N / 4 : N; }
 
-template <class F, int RNG, bool SH, int THREADS, int MINB, int TMA = 0, int WIN = 0, bool SHFL = true>
+// ONCHIP (tuning flavour, N = 256): the pass-1 -> pass-2 intermediate T lives in shared memory
+// (n_pup x (N + 1) complex, one CTA per SM) instead of the CTA-private global slot.
+template <class F, int RNG, bool SH, int THREADS, int MINB, int TMA = 0, int WIN = 0, bool SHFL = true,
+          bool ONCHIP = false>
 __global__ void __launch_bounds__(THREADS, MINB) screen_detect_radix(const __grid_constant__ RunArgs a) {
     constexpr int N = F::N, S1 = F::S1, E = F::E, LPB = THREADS / S1;
+    constexpr int NP = N + 1;                                   // row stride of the on-chip T
     static_assert(THREADS % S1 == 0 && LPB >= 1 && (S1 <= 32 || LPB <= 15), "line/barrier layout");
     static_assert(E == 16 || E == 32, "elements per thread");
     constexpr unsigned kKeep = WIN == 0 ? 0xffffffffu : keep_mask<F>(window_half<N>(WIN));
@@ -426,7 +432,7 @@ __global__ void __launch_bounds__(THREADS, MINB) screen_detect_radix(const __gri
     Tw* twb = twa + F::kTwA;
     float2* bufs = reinterpret_cast<float2*>(twb + F::kTwB);
     // pass-1 output staging: per line slot R = 2^stage_shift (1 or 2) planes of n_pup kept outputs
-    const int rs = kTma ? 0 : a.stage_shift, R = 1 << rs;
+    const int rs = (kTma || ONCHIP) ? 0 : a.stage_shift, R = 1 << rs;
     float2* tiles = bufs + LPB * F::kBuf;
     unsigned char* stage_all = reinterpret_cast<unsigned char*>(tiles + (rs ? LPB * R * a.n_pup : 0));
     uint64_t* bars = reinterpret_cast<uint64_t*>(stage_all + (kTma ? kWarps * kStageBytes : 0));
@@ -434,6 +440,7 @@ __global__ void __launch_bounds__(THREADS, MINB) screen_detect_radix(const __gri
     float* red = reinterpret_cast<float*>(st + kStatWords);
     float2* sh_amp = reinterpret_cast<float2*>(red + 4 * kWarps);     // SH only
     float2* sh_tab = sh_amp + 28;
+    float2* Ts = sh_amp + (SH ? 28 + kShTab * a.n_pup : 0);           // ONCHIP only: n_pup x NP
 
     const int tid = threadIdx.x;
     const int ln = tid / S1, u = tid % S1;
@@ -458,7 +465,8 @@ __global__ void __launch_bounds__(THREADS, MINB) screen_detect_radix(const __gri
     __syncthreads();
 
     float2* T = a.scratch + (size_t)blockIdx.x * N * P;
-    const int n1 = N / LPB, n2 = (P + LPB - 1) / LPB;
+    const int n1 = (N + LPB - 1) / LPB, n2 = (P + LPB - 1) / LPB;
+    static_assert(ONCHIP || N % LPB == 0, "rows per iteration");
 
     static_assert(F::k_off_all_even(), "the output sign is taken per thread: k_off must be even");
     // which of this thread's E outputs fall inside the crop [lo, lo+P): the same for every line
@@ -510,6 +518,7 @@ __global__ void __launch_bounds__(THREADS, MINB) screen_detect_radix(const __gri
             // last column iteration: warps whose lines all lie beyond the crop have nothing to do
             // (line barriers involve only the threads of that line)
             if (!rows && line - (ln % kLinesPerWarp) >= P) continue;
+            if (ONCHIP && rows && line - (ln % kLinesPerWarp) >= N) continue;     // partial last row iteration
 
             float2 v[E];
             const bool staged = (rows && kTmaW) || (!rows && kTmaT);
@@ -591,6 +600,10 @@ __global__ void __launch_bounds__(THREADS, MINB) screen_detect_radix(const __gri
                 for (int m = 0; m < E; ++m) v[m] = ts[u + S1 * m];
                 __syncwarp();
                 if (it + 1 < n1 + n2) prefetch(it + 1);
+            } else if (ONCHIP) {
+                const float2* tcol = Ts + (size_t)(line < P ? line : 0) * NP;
+#pragma unroll
+                for (int m = 0; m < E; ++m) v[m] = tcol[u + S1 * m];
             } else {
                 const float2* tcol = T + (size_t)(line < P ? line : 0) * N;
 #pragma unroll
@@ -600,7 +613,12 @@ __global__ void __launch_bounds__(THREADS, MINB) screen_detect_radix(const __gri
             if constexpr (kShfl) F::template run_shfl<kKeep>(u, v, twa, twb, buf, sync);
             else F::run(u, v, twa, twb, buf, sync);
 
-            if (rows && rs == 0) {
+            if (ONCHIP && rows) {
+                float2* tb = Ts + (kb * NP + line);           // &Ts[(k - lo) * NP + r'] at k_off = 0
+#pragma unroll
+                for (int e = 0; e < E; ++e)
+                    if (((kKeep >> e) & 1u) && (need & (1u << e))) tb[F::k_off(e) * NP] = v[e];
+            } else if (rows && rs == 0) {
                 float2* tb = T + ((long long)kb * N + line);  // &T[(k - lo) * N + r'] at k_off = 0
 #pragma unroll
                 for (int e = 0; e < E; ++e)
@@ -873,8 +891,39 @@ inline int launch_kernel(void (*kern)(RunArgs), const RunArgs& args, int threads
     long long grid = (long long)per_sm * sms;
     if (grid > args.n_pairs) grid = args.n_pairs;
     if (grid > max_grid) grid = max_grid;
+    bool windowed = false;
+    if (g_l2_persist) {
+        // keep the CTA-private pass-1 -> pass-2 intermediate in L2: persisting window over the slots in use
+        int dev = 0, max_win = 0, max_persist = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+        size_t bytes = (size_t)grid * args.n * args.n_pup * sizeof(float2);
+        if (max_win > 0 && max_persist > 0) {
+            static int limit_set_for = -1;
+            if (limit_set_for != dev) {
+                cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
+                limit_set_for = dev;
+            }
+            cudaStreamAttrValue attr = {};
+            attr.accessPolicyWindow.base_ptr = (void*)args.scratch;
+            attr.accessPolicyWindow.num_bytes = bytes < (size_t)max_win ? bytes : (size_t)max_win;
+            attr.accessPolicyWindow.hitRatio = bytes <= (size_t)max_persist ? 1.0f : (float)max_persist / (float)bytes;
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            windowed = cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess;
+            cudaGetLastError();
+        }
+    }
     kern<<<(unsigned)grid, threads, smem, st>>>(args);
-    return check_launch(what);
+    const int rc_launch = check_launch(what);
+    if (windowed) {
+        cudaStreamAttrValue attr = {};
+        attr.accessPolicyWindow.num_bytes = 0;
+        cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
+        cudaGetLastError();
+    }
+    return rc_launch;
 }
 
 // Launch one radix instance; decides on the two-row store staging (N <= 512: +1 % at N = 256, +4 % at

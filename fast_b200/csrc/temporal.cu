@@ -1,10 +1,18 @@
 // K4: TEMPORAL (frozen-flow) mode.  Contract and reference citations: include/fastb.h.
-//   K4a  layer screens: direct 2-D inverse DFT (any even N), real part, once per simulation.
+//   K4a  layer screens, once per simulation: two passes of line FFTs (layer_screens_fft.cu: radix for
+//        powers of two, chirp-z for other even N <= 1024); the direct 2-D inverse DFT below serves the
+//        remaining sizes (any even N <= 4096).
 //   K4b  per time step: bilinear gather of the L layer screens at the wind-shifted pupil
 //        coordinates, layer sum, detector -- one scalar per step reaches HBM.
 #include "fastb_common.cuh"
 
 namespace fastb {
+
+bool layer_fft_ok(int n);
+size_t layer_fft_workspace_bytes(int n, int L);
+int layer_screens_fft(int n, int L, unsigned long long seed, const float* weight, const float* noise, float* screens,
+                      void* workspace, cudaStream_t st);
+
 namespace {
 
 constexpr int kThreads = 256;
@@ -159,6 +167,7 @@ using namespace fastb;
 
 extern "C" int64_t fastb_layer_screens_workspace_bytes(int32_t n, int32_t n_layers) {
     if (n < 2 || n_layers < 1) return 0;
+    if (layer_fft_ok(n)) return (int64_t)layer_fft_workspace_bytes(n, n_layers);
     return (int64_t)sizeof(float2) * ((int64_t)n + (int64_t)n_layers * n * n);
 }
 
@@ -171,6 +180,8 @@ extern "C" int fastb_layer_screens(int32_t n, int32_t n_layers, uint64_t seed, c
     FASTB_REQUIRE(workspace_bytes >= fastb_layer_screens_workspace_bytes(n, n_layers),
                   "fastb_layer_screens: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
+    if (layer_fft_ok(n))
+        return layer_screens_fft(n, n_layers, seed, d_weight_per_layer, d_noise, d_screens, d_workspace, st);
     float2* tw = (float2*)d_workspace;
     float2* T = tw + n;
     twiddle_f32_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, tw);

@@ -9,6 +9,9 @@
 //   FASTB_STAGE=0|1                       two-row store staging off / on
 //   FASTB_TMA=1|2|3                       cp.async.bulk staging of weights+scratch / scratch / weights
 //   FASTB_E=32                            32 elements per thread (N = 512, 1024)
+//   FASTB_L2PERSIST=1                     persisting-L2 access-policy window over the scratch slots
+//   FASTB_ONCHIP=<threads>                N = 256 only: pass-1 -> pass-2 intermediate in shared memory, one CTA
+//                                         of 256 / 384 threads per SM (no global scratch traffic at all)
 // Serves the device-RNG, no-sub-harmonics instances of N = 256, 512, 1024 whose crop is the standard
 // centred one (window class 2, 2, 1); anything else falls through to the product selection.
 #include "../screen_detect_kernel.cuh"
@@ -51,6 +54,24 @@ int tune_size(const RunArgs& a, const RadixRequest& rq, cudaStream_t st) {
     const int shfl = env_int("FASTB_SHFL", 1), keep = env_int("FASTB_KEEP", 1);
     const int stage = env_int("FASTB_STAGE", LOG2N <= 9 ? 1 : 0), tma = env_int("FASTB_TMA", 0);
     const int e = env_int("FASTB_E", 16);
+    if constexpr (LOG2N == 8) {
+        const int onchip = env_int("FASTB_ONCHIP", 0);
+        if (onchip) {
+            const int c0 = F::N / 2, h0 = (c0 - a.lo) > (a.lo + a.n_pup - c0) ? (c0 - a.lo) : (a.lo + a.n_pup - c0);
+            if (!(a.lo <= c0 && a.lo + a.n_pup >= c0 && h0 <= window_half<F::N>(WIN))) return -1;
+            void (*ko)(RunArgs) = nullptr;
+            if (onchip == 384) ko = rq.rng == kRngFast ? screen_detect_radix<F, kRngFast, false, 384, 1, 0, WIN, true, true>
+                                                        : screen_detect_radix<F, kRngPhilox, false, 384, 1, 0, WIN, true, true>;
+            else if (onchip == 256) ko = rq.rng == kRngFast ? screen_detect_radix<F, kRngFast, false, 256, 1, 0, WIN, true, true>
+                                                            : screen_detect_radix<F, kRngPhilox, false, 256, 1, 0, WIN, true, true>;
+            if (!ko) return -1;
+            const size_t smem = radix_smem_bytes<F>(false, a.n_pup, onchip, false) + sizeof(float2) * (size_t)a.n_pup * (F::N + 1);
+            if (smem > 227 * 1024) return -1;
+            RunArgs a2 = a;
+            a2.stage_shift = 0;
+            return launch_kernel(ko, a2, onchip, smem, rq.max_grid, st, "screen_detect_radix(onchip)");
+        }
+    }
     if (!shape && shfl && keep && stage == (LOG2N <= 9 ? 1 : 0) && !tma && e == 16) return -1;
     // the crop must be the one the window class was chosen for
     const int c = F::N / 2, half = (c - a.lo) > (a.lo + a.n_pup - c) ? (c - a.lo) : (a.lo + a.n_pup - c);
@@ -99,7 +120,10 @@ int tune_hook(int log2n, const RunArgs& a, const RadixRequest& rq, cudaStream_t 
 }
 
 struct Registrar {
-    Registrar() { g_tune_hook = tune_hook; }
+    Registrar() {
+        g_tune_hook = tune_hook;
+        g_l2_persist = env_int("FASTB_L2PERSIST", 0);      // FASTB_L2PERSIST=1: persisting L2 window over the scratch
+    }
 } g_registrar;
 
 }  // namespace

@@ -206,7 +206,8 @@ class Fast():
             return (0.423 * (2 * numpy.pi / lam) ** 2 * cn2_sum) ** (-3. / 5.)
 
         def theta0_of(cn2, h, lam):
-            return 0.057 * lam ** (6. / 5.) * numpy.sum(cn2 * h ** (5. / 3.)) ** (-3. / 5.)
+            # arcseconds, like aotools.isoplanaticAngle (attribute / FITS header only, not used by the MC)
+            return 0.057 * lam ** (6. / 5.) * numpy.sum(cn2 * h ** (5. / 3.)) ** (-3. / 5.) * 180. * 3600. / numpy.pi
 
         def tau0_of(cn2, v, lam):
             return float(numpy.sum(cn2 * v ** (5. / 3.)) ** (-3. / 5.) * 0.057 * lam ** (6. / 5.))

@@ -309,8 +309,9 @@ int fastb_rng_dump_mode(uint64_t seed, int64_t pair, int32_t n, int32_t rng_fast
  *   d_noise             NULL (device Philox; layer l uses pair index FASTB_LAYER_PAIR_BASE + l,
  *                       same cell mapping as fastb_screen_detect) or L*N*N complex64
  *   d_screens           L*N*N float
- * Any even N <= 4096: pruning does not apply (the whole screen is needed), and this runs once
- * per simulation, so it is a direct O(N^3) DFT in fp32.
+ * Any even N <= 4096: pruning does not apply (the whole screen is needed).  Two passes of N-point line
+ * transforms: the register radix FFT for N = 64..2048 powers of two, the chirp-z convolution for any
+ * other even N <= 1024 (e.g. the reference's auto-sized 164); a direct DFT serves the remaining sizes.
  *
  * K4b fastb_temporal_detect: the per-step body (fast/fast.py:619-633) fused with
  * Fast.compute_detector (fast/fast.py:647-668).  For step j and pupil pixel (a, b)

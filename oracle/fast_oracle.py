@@ -136,10 +136,10 @@ def atmosphere(p):
     out = dict(gamma=gamma, h=h, cn2=cn2, L=L, dtheta=dtheta, paa=paa, wind_dir=wdir,
                wind_vector=wind, wind_speed=speed,
                r0=(0.423 * k500 ** 2 * cn2_0.sum()) ** (-3 / 5),
-               theta0=0.057 * 500e-9 ** (6 / 5) * np.sum(cn2_0 * h_0 ** (5 / 3)) ** (-3 / 5),
+               theta0=0.057 * 500e-9 ** (6 / 5) * np.sum(cn2_0 * h_0 ** (5 / 3)) ** (-3 / 5) * 180.0 * 3600.0 / np.pi,
                tau0=float(np.sum(cn2_0 * w_0 ** (5 / 3)) ** (-3 / 5) * 0.057 * 500e-9 ** (6 / 5)),
                r0_los=(0.423 * kw ** 2 * cn2.sum()) ** (-3 / 5),
-               theta0_los=0.057 * p['WVL'] ** (6 / 5) * np.sum(cn2 * h ** (5 / 3)) ** (-3 / 5),
+               theta0_los=0.057 * p['WVL'] ** (6 / 5) * np.sum(cn2 * h ** (5 / 3)) ** (-3 / 5) * 180.0 * 3600.0 / np.pi,
                tau0_los=float(np.sum(cn2 * speed ** (5 / 3)) ** (-3 / 5) * 0.057 * p['WVL'] ** (6 / 5)))
     return out
 

@@ -54,7 +54,10 @@ def cn2_to_r0(cn2, lamda=500.e-9):
 
 
 def isoplanaticAngle(cn2, h, lamda=500.e-9):
-    return 0.057 * lamda ** (6.0 / 5.0) * _np.sum(cn2 * h ** (5.0 / 3.0)) ** (-3.0 / 5.0)
+    # aotools.turbulence.atmos_conversions: returns ARCSECONDS (restated from memory like the rest of this
+    # shim; unverifiable offline -- the value only feeds the `theta0` attribute / FITS header)
+    Jsum = (cn2 * (h ** (5.0 / 3.0))).sum()
+    return 0.057 * lamda ** (6.0 / 5.0) * Jsum ** (-3.0 / 5.0) * 180.0 * 3600.0 / _np.pi
 
 
 def coherenceTime(cn2, v, lamda=500.e-9):

@@ -439,6 +439,25 @@ def test_temporal_device_rng_screens_match_oracle(fast):
     assert not np.array_equal(fast.Fast(dict(p, SEED=32)).run()._r, res._r)
 
 
+@pytest.mark.parametrize('N', [64, 100, 164, 256, 300, 1000, 1024, 1100])
+def test_layer_screens_every_size_class_matches_oracle(fast, N):
+    """K4a: radix line FFT (powers of two), chirp-z (other even N <= 1024) and the direct DFT (the rest)
+    against the numpy restatement of make_phase_fft(double=False), host noise and device RNG."""
+    lib = fast._lib
+    L = 2
+    rng = np.random.default_rng(N)
+    W = rng.random((L, N, N)) * 1e-4
+    df = 0.7
+    noise = (rng.normal(size=(L, N, N)) + 1j * rng.normal(size=(L, N, N))).astype(np.complex64)
+    weight = lib.make_weight(torch.from_numpy(W).cuda(), df)
+    got = lib.layer_screens(weight, 5, noise=torch.from_numpy(noise).cuda()).cpu().numpy()
+    want = fo.layer_screens(noise.astype(complex), W, df)
+    assert rel(got, want) < 2e-5
+    got_rng = lib.layer_screens(weight, 5).cpu().numpy()
+    dev_noise = np.stack([fo.device_noise_pair(5, (1 << 62) + l, N) for l in range(L)])
+    assert rel(got_rng, fo.layer_screens(dev_noise, W, df)) < 2e-5
+
+
 # ---------------------------------------------------------------------------------------------
 # sub-harmonics (SUBHARM=True)
 # ---------------------------------------------------------------------------------------------
