@@ -15,12 +15,14 @@ HERE = os.path.join(ROOT, 'fast_b200')
 CSRC = os.path.join(HERE, 'csrc')
 # tuning builds (FASTB_TUNE=1) go to their own library so that the product .so is never replaced by one
 TUNE = bool(os.environ.get('FASTB_TUNE'))
-LIB = os.path.join(HERE, 'libfastb_tune.so' if TUNE else 'libfastb.so')
-STAMP = os.path.join(HERE, 'build', 'libfastb_tune.stamp' if TUNE else 'libfastb.stamp')
+LIB = os.path.join(HERE, ('libfastb_tune%s.so' % os.environ.get('FASTB_TUNE_TAG', '')) if TUNE else 'libfastb.so')
+STAMP = os.path.join(HERE, 'build', ('libfastb_tune%s.stamp' % os.environ.get('FASTB_TUNE_TAG', '')) if TUNE else 'libfastb.stamp')
 ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
 COMMON = ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']
 # per-file extra flags: the PSD kernel follows numpy's operation order (no FMA contraction)
 _DBG = ['-DFASTB_TUNE_DBG'] if os.environ.get('FASTB_TUNE_DBG') else []
+if os.environ.get('FASTB_SCALAR_STAGES'):      # tuning builds: which FFT stages use scalar FP32 (fft_core.cuh)
+    _DBG += ['-DFASTB_SCALAR_STAGES=' + os.environ['FASTB_SCALAR_STAGES']]
 # object name -> (source, extra flags).  The radix kernels of K2 are compiled once per grid size
 # (N = 2^6 .. 2^11) so that the ~20 instances of each size build in parallel.
 SOURCES = {
@@ -52,6 +54,7 @@ def _digest():
     h.update(repr(SOURCES).encode())
     h.update(os.environ.get('FASTB_TUNE', '').encode())
     h.update(os.environ.get('FASTB_TUNE_DBG', '').encode())
+    h.update(os.environ.get('FASTB_SCALAR_STAGES', '').encode())
     return h.hexdigest()
 
 
@@ -62,7 +65,7 @@ def build(force=False, verbose=False):
     if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read() == dig:
         return LIB
     nvcc = os.environ.get('NVCC', 'nvcc')
-    objdir = os.path.join(HERE, 'build', 'tune' if TUNE else 'product')
+    objdir = os.path.join(HERE, 'build', ('tune' + os.environ.get('FASTB_TUNE_TAG', '')) if TUNE else 'product')
     os.makedirs(objdir, exist_ok=True)
     objs = []
     procs = []

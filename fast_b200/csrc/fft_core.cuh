@@ -120,6 +120,18 @@ FASTB_HD pc cmulc(pc a, float c, float s) {
     return pc{fnma2(a.im, bc2(s), mul2(a.re, bc2(c))), fma2(a.re, bc2(s), mul2(a.im, bc2(c)))};
 }
 
+// one line, scalar FP32 (tuning flavour FASTB_SCALAR_STAGES): the same arithmetic as float2 but as
+// FADD / FMUL / FFMA, which may issue on either FMA pipe -- packed instructions occupy the heavy pipe alone
+struct sc {
+    float x, y;
+};
+FASTB_HD sc cadd(sc a, sc b) { return sc{a.x + b.x, a.y + b.y}; }
+FASTB_HD sc csub(sc a, sc b) { return sc{a.x - b.x, a.y - b.y}; }
+FASTB_HD sc caddi(sc a, sc b) { return sc{a.x - b.y, a.y + b.x}; }
+FASTB_HD sc csubi(sc a, sc b) { return sc{a.x + b.y, a.y - b.x}; }
+FASTB_HD sc cmuli(sc a) { return sc{-a.y, a.x}; }
+FASTB_HD sc cmulc(sc a, float c, float s) { return sc{fmaf(-a.y, s, a.x * c), fmaf(a.x, s, a.y * c)}; }
+
 // ---- small DFTs (inverse sign), natural order in and out -------------------------------------
 template <class V>
 FASTB_HD void dft4(V& x0, V& x1, V& x2, V& x3) {            // y_k = sum_n x_n i^(n k)
@@ -319,8 +331,27 @@ struct LineFFT {
     }
 
     // phase A: dft16 over m, twiddle, write exchange buffer
-    FASTB_HD static void phase_a(int t, V (&v)[16], const Tw* twa, float2* buf) {
+    // FASTB_SCALAR_STAGES (tuning builds): bit 0 = phase A, bit 1 = phase B butterflies in scalar FP32
+    FASTB_HD static void dft16_stage(V (&v)[16], int stage_bit) {
+#ifdef FASTB_SCALAR_STAGES
+        if constexpr (TwOf<V>::kLines == 1) {
+            if ((FASTB_SCALAR_STAGES) & stage_bit) {
+                sc t[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) t[i] = sc{v[i].x, v[i].y};
+                dft16(t);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = make_float2(t[i].x, t[i].y);
+                return;
+            }
+        }
+#endif
+        (void)stage_bit;
         dft16(v);
+    }
+
+    FASTB_HD static void phase_a(int t, V (&v)[16], const Tw* twa, float2* buf) {
+        dft16_stage(v, 1);
         apply_twiddle_row(v, twa + t * kTwRow);
         if (kThree) {
 #pragma unroll
@@ -341,7 +372,7 @@ struct LineFFT {
 #pragma unroll
             for (int m2 = 0; m2 < 16; ++m2) v[m2] = Smem<V>::get(buf, kPlane, a * (S1 + kPadA) + t2 + S2 * m2);
         }
-        dft16(v);
+        dft16_stage(v, 2);
         if (S2 > 1) apply_twiddle_row(v, twb + t2 * kTwRow);
     }
 

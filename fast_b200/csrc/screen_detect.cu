@@ -8,6 +8,7 @@ namespace fastb {
 
 TuneHook g_tune_hook = nullptr;
 int g_l2_persist = 0;
+int g_stagger = 0, g_wstagger = 0;
 
 #define FASTB_DECL_SIZE(k)                                                                    \
     int launch_radix_##k(const RunArgs& a, const RadixRequest& rq, cudaStream_t st);         \

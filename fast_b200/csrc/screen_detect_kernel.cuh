@@ -62,6 +62,9 @@ struct RunArgs {
     const float2* sh_mean;    // 27
     float* phs;               // direct kernel only: write the cropped screens instead of detecting
     int dbg;                  // tuning builds: timing experiments (results wrong); 0 in the product
+    // phase staggering (radix kernel; 0 = off): co-resident CTAs start `stagger` cycles apart per residency
+    // slot (blockIdx / sms), the warps that share a scheduler inside one CTA `wstagger` cycles apart per pass
+    int stagger, wstagger, sms;
 };
 #ifdef FASTB_TUNE_DBG
 #define FASTB_DBG(a, bit) ((a).dbg & (bit))
@@ -86,6 +89,8 @@ typedef int (*TuneHook)(int log2n, const RunArgs& a, const RadixRequest& rq, cud
 extern TuneHook g_tune_hook;
 // L2 residency hint for the scratch slots (launch_kernel): 0 off, 1 persisting access-policy window
 extern int g_l2_persist;
+// phase staggering in cycles (RunArgs.stagger / wstagger), 0 = off
+extern int g_stagger, g_wstagger;
 
 namespace {
 
@@ -410,8 +415,9 @@ constexpr int window_half(int win) { return win == 1 ? N / 8 : win == 2 ? 3 * N 
 
 // ONCHIP (tuning flavour, N = 256): the pass-1 -> pass-2 intermediate T lives in shared memory
 // (n_pup x (N + 1) complex, one CTA per SM) instead of the CTA-private global slot.
+// STAGE: two-row store staging of pass 1 fixed at compile time (0 / 1), or -1 = RunArgs.stage_shift decides.
 template <class F, int RNG, bool SH, int THREADS, int MINB, int TMA = 0, int WIN = 0, bool SHFL = true,
-          bool ONCHIP = false>
+          bool ONCHIP = false, int STAGE = -1>
 __global__ void __launch_bounds__(THREADS, MINB) screen_detect_radix(const __grid_constant__ RunArgs a) {
     constexpr int N = F::N, S1 = F::S1, E = F::E, LPB = THREADS / S1;
     constexpr int NP = N + 1;                                   // row stride of the on-chip T
@@ -432,7 +438,7 @@ __global__ void __launch_bounds__(THREADS, MINB) screen_detect_radix(const __gri
     Tw* twb = twa + F::kTwA;
     float2* bufs = reinterpret_cast<float2*>(twb + F::kTwB);
     // pass-1 output staging: per line slot R = 2^stage_shift (1 or 2) planes of n_pup kept outputs
-    const int rs = (kTma || ONCHIP) ? 0 : a.stage_shift, R = 1 << rs;
+    const int rs = (kTma || ONCHIP) ? 0 : (STAGE >= 0 ? STAGE : a.stage_shift), R = 1 << rs;
     float2* tiles = bufs + LPB * F::kBuf;
     unsigned char* stage_all = reinterpret_cast<unsigned char*>(tiles + (rs ? LPB * R * a.n_pup : 0));
     uint64_t* bars = reinterpret_cast<uint64_t*>(stage_all + (kTma ? kWarps * kStageBytes : 0));
@@ -463,6 +469,11 @@ __global__ void __launch_bounds__(THREADS, MINB) screen_detect_radix(const __gri
     if (tid == 0) stats_reset(st, 0);
     if (kTma) fence_proxy_async();            // mbarrier init visible to the async proxy
     __syncthreads();
+    auto spin = [](long long cycles) {
+        const long long t0 = clock64();
+        while (clock64() - t0 < cycles) {}
+    };
+    if (a.stagger) spin((long long)(blockIdx.x / a.sms) * a.stagger);
 
     float2* T = a.scratch + (size_t)blockIdx.x * N * P;
     const int n1 = (N + LPB - 1) / LPB, n2 = (P + LPB - 1) / LPB;
@@ -503,12 +514,14 @@ __global__ void __launch_bounds__(THREADS, MINB) screen_detect_radix(const __gri
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
         if (SH) sh_prepare(a, pair, id, sh_amp, sh_tab);   // table visible after the barrier at it == n1
         if (kTma) prefetch(0);
+        if (kWarps > 4 && a.wstagger) spin((long long)(warp >> 2) * a.wstagger);
         for (int it = 0; it < n1 + n2; ++it) {
             const bool rows = it < n1;
             if (it == n1) {
                 if (kTmaT) fence_proxy_async();       // T was written through the generic proxy
                 __syncthreads();                      // every row of T is stored before a column is read
                 if (kTma) prefetch(n1);
+                if (kWarps > 4 && a.wstagger) spin((long long)(warp >> 2) * a.wstagger);
             }
             // pass 1: a line slot takes R (1 or 2) consecutive rows in R consecutive iterations, so
             // that its kept outputs leave as 16-byte stores of two adjacent rows per column
@@ -635,10 +648,25 @@ __global__ void __launch_bounds__(THREADS, MINB) screen_detect_radix(const __gri
                     // FFT, so no barrier is needed after the reads.
                     sync();
                     float2* tr = T + (line - (R - 1));
+                    if constexpr (WIN != 0) {
+                        // the window class bounds the crop width: a fixed number of predicated column
+                        // steps instead of a counted loop (its control flow was 2.3 % of all instructions)
+                        constexpr int kSteps = (2 * window_half<N>(WIN) + S1 - 1) / S1;
+#pragma unroll
+                        for (int j = 0; j < kSteps; ++j) {
+                            const int c = u + j * S1;
+                            if (c < P) {
+                                const float2 x0 = tile[c], x1 = tile[P + c];
+                                __stcg(reinterpret_cast<float4*>(tr + (long long)c * N),
+                                       make_float4(x0.x, x0.y, x1.x, x1.y));
+                            }
+                        }
+                    } else {
 #pragma unroll 2
-                    for (int c = u; c < P; c += S1) {
-                        const float2 x0 = tile[c], x1 = tile[P + c];
-                        __stcg(reinterpret_cast<float4*>(tr + (long long)c * N), make_float4(x0.x, x0.y, x1.x, x1.y));
+                        for (int c = u; c < P; c += S1) {
+                            const float2 x0 = tile[c], x1 = tile[P + c];
+                            __stcg(reinterpret_cast<float4*>(tr + (long long)c * N), make_float4(x0.x, x0.y, x1.x, x1.y));
+                        }
                     }
                 }
             } else if (line < P) {
@@ -891,6 +919,10 @@ inline int launch_kernel(void (*kern)(RunArgs), const RunArgs& args, int threads
     long long grid = (long long)per_sm * sms;
     if (grid > args.n_pairs) grid = args.n_pairs;
     if (grid > max_grid) grid = max_grid;
+    RunArgs launch_args = args;
+    launch_args.sms = sms;
+    launch_args.stagger = g_stagger;
+    launch_args.wstagger = g_wstagger;
     bool windowed = false;
     if (g_l2_persist) {
         // keep the CTA-private pass-1 -> pass-2 intermediate in L2: persisting window over the slots in use
@@ -915,7 +947,7 @@ inline int launch_kernel(void (*kern)(RunArgs), const RunArgs& args, int threads
             cudaGetLastError();
         }
     }
-    kern<<<(unsigned)grid, threads, smem, st>>>(args);
+    kern<<<(unsigned)grid, threads, smem, st>>>(launch_args);
     const int rc_launch = check_launch(what);
     if (windowed) {
         cudaStreamAttrValue attr = {};
@@ -930,12 +962,16 @@ inline int launch_kernel(void (*kern)(RunArgs), const RunArgs& args, int threads
 // N = 512, -2 % at N = 1024 in same-box A/B) unless the extra shared memory would cost a resident CTA.
 template <class F>
 int launch_radix_instance(void (*kern)(RunArgs), const RunArgs& args, int threads, bool use_tma, int want_stage,
-                          int max_grid, cudaStream_t st) {
+                          int max_grid, cudaStream_t st, bool stage_fixed = false) {
     const bool sh = args.sh_weight != nullptr;
     RunArgs a2 = args;
     a2.stage_shift = 0;
     size_t smem = radix_smem_bytes<F>(sh, args.n_pup, threads, use_tma);
     const size_t smem2 = radix_smem_bytes<F>(sh, args.n_pup, threads, false, 1);
+    if (stage_fixed) {           // the instance was compiled with STAGE = want_stage
+        a2.stage_shift = want_stage;
+        return launch_kernel(kern, a2, threads, want_stage ? smem2 : smem, max_grid, st);
+    }
     if (!use_tma && want_stage && (F::N / (threads / F::S1)) % 2 == 0 && smem2 <= 227 * 1024) {
         int occ0 = 0, occ = 0;
         FASTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));

@@ -17,8 +17,13 @@ using Cfg = RadixCfg<kLog2N, 16>;
 using F = Cfg::F;
 constexpr int T = Cfg::kThreadsPerCta, M = Cfg::kMinBlocks;
 
+// N <= 512: two rows staged per line slot and stored as one 16-byte word per column (compile-time: the
+// staging tiles of the product shapes always fit, 32 KB / 201 KB at the widest crop)
+constexpr int kStage = kLog2N <= 9 ? 1 : 0;
+static_assert((F::N / (T / F::S1)) % 2 == 0, "row iterations come in pairs");
+
 template <int RNG, bool SH, int WIN>
-constexpr auto kern() { return screen_detect_radix<F, RNG, SH, T, M, 0, WIN>; }
+constexpr auto kern() { return screen_detect_radix<F, RNG, SH, T, M, 0, WIN, true, false, kStage>; }
 
 // Window-specialised instances (no sub-harmonics): the smallest centred window class that
 // contains the crop.  FAST's pupil crop is centred and 1/6 .. 1/3 of the grid wide.
@@ -58,7 +63,7 @@ int FASTB_CAT(launch_radix_, FASTB_LOG2N)(const RunArgs& a, const RadixRequest& 
         const int rc = prepare_weight_s(F::N, a.n_items > 1 ? a.n_items : 1, a.weight, a.weight_s, st);
         if (rc) return rc;
     }
-    return launch_radix_instance<F>(k, a, T, false, kLog2N <= 9 ? 1 : 0, rq.max_grid, st);
+    return launch_radix_instance<F>(k, a, T, false, kStage, rq.max_grid, st, true);
 }
 
 // line-pair kernel: N <= 256: 128 threads x 5 CTAs/SM (96 registers); above: 256 x 2 (128 registers)

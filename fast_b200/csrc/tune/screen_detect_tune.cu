@@ -10,6 +10,7 @@
 //   FASTB_TMA=1|2|3                       cp.async.bulk staging of weights+scratch / scratch / weights
 //   FASTB_E=32                            32 elements per thread (N = 512, 1024)
 //   FASTB_L2PERSIST=1                     persisting-L2 access-policy window over the scratch slots
+//   FASTB_STAGGER=<cycles>, FASTB_WSTAGGER=<cycles>   phase staggering of co-resident CTAs / same-scheduler warps
 //   FASTB_ONCHIP=<threads>                N = 256 only: pass-1 -> pass-2 intermediate in shared memory, one CTA
 //                                         of 256 / 384 threads per SM (no global scratch traffic at all)
 // Serves the device-RNG, no-sub-harmonics instances of N = 256, 512, 1024 whose crop is the standard
@@ -123,6 +124,8 @@ struct Registrar {
     Registrar() {
         g_tune_hook = tune_hook;
         g_l2_persist = env_int("FASTB_L2PERSIST", 0);      // FASTB_L2PERSIST=1: persisting L2 window over the scratch
+        g_stagger = env_int("FASTB_STAGGER", 0);           // cycles between the start of co-resident CTAs
+        g_wstagger = env_int("FASTB_WSTAGGER", 0);         // cycles between same-scheduler warps of a CTA, per pass
     }
 } g_registrar;
 
