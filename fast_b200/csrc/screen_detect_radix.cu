@@ -22,8 +22,12 @@ constexpr int T = Cfg::kThreadsPerCta, M = Cfg::kMinBlocks;
 constexpr int kStage = kLog2N <= 9 ? 1 : 0;
 static_assert((F::N / (T / F::S1)) % 2 == 0, "row iterations come in pairs");
 
+// last FFT stage on warp shuffles where it measured faster: the radix-2 stage of N = 512 (+5.4 %); the
+// radix-4 stage of N = 1024 is 0.5 - 1 % slower than the shared-memory exchange (profiles/experiments_r02.txt)
+constexpr bool kShuffle = F::S2 == 2;
+
 template <int RNG, bool SH, int WIN>
-constexpr auto kern() { return screen_detect_radix<F, RNG, SH, T, M, 0, WIN, true, false, kStage>; }
+constexpr auto kern() { return screen_detect_radix<F, RNG, SH, T, M, 0, WIN, kShuffle, false, kStage>; }
 
 // Window-specialised instances (no sub-harmonics): the smallest centred window class that
 // contains the crop.  FAST's pupil crop is centred and 1/6 .. 1/3 of the grid wide.
