@@ -648,16 +648,6 @@ __global__ void __launch_bounds__(THREADS, MINB) screen_detect_radix(const __gri
                     // FFT, so no barrier is needed after the reads.
                     sync();
                     float2* tr = T + (line - (R - 1));
-                    // column c gets its R consecutive rows as R/2 adjacent 16-byte stores (R = 4: one full sector)
-                    auto flush_col = [&](int c) {
-                        const float2 x0 = tile[c], x1 = tile[P + c];
-                        float4* dst = reinterpret_cast<float4*>(tr + (long long)c * N);
-                        __stcg(dst, make_float4(x0.x, x0.y, x1.x, x1.y));
-                        if (rs == 2) {
-                            const float2 x2 = tile[2 * P + c], x3 = tile[3 * P + c];
-                            __stcg(dst + 1, make_float4(x2.x, x2.y, x3.x, x3.y));
-                        }
-                    };
                     if constexpr (WIN != 0) {
                         // the window class bounds the crop width: a fixed number of predicated column
                         // steps instead of a counted loop (its control flow was 2.3 % of all instructions)
@@ -665,11 +655,18 @@ __global__ void __launch_bounds__(THREADS, MINB) screen_detect_radix(const __gri
 #pragma unroll
                         for (int j = 0; j < kSteps; ++j) {
                             const int c = u + j * S1;
-                            if (c < P) flush_col(c);
+                            if (c < P) {
+                                const float2 x0 = tile[c], x1 = tile[P + c];
+                                __stcg(reinterpret_cast<float4*>(tr + (long long)c * N),
+                                       make_float4(x0.x, x0.y, x1.x, x1.y));
+                            }
                         }
                     } else {
 #pragma unroll 2
-                        for (int c = u; c < P; c += S1) flush_col(c);
+                        for (int c = u; c < P; c += S1) {
+                            const float2 x0 = tile[c], x1 = tile[P + c];
+                            __stcg(reinterpret_cast<float4*>(tr + (long long)c * N), make_float4(x0.x, x0.y, x1.x, x1.y));
+                        }
                     }
                 }
             } else if (line < P) {
@@ -970,12 +967,12 @@ int launch_radix_instance(void (*kern)(RunArgs), const RunArgs& args, int thread
     RunArgs a2 = args;
     a2.stage_shift = 0;
     size_t smem = radix_smem_bytes<F>(sh, args.n_pup, threads, use_tma);
-    const size_t smem2 = radix_smem_bytes<F>(sh, args.n_pup, threads, false, want_stage > 0 ? want_stage : 1);
+    const size_t smem2 = radix_smem_bytes<F>(sh, args.n_pup, threads, false, 1);
     if (stage_fixed) {           // the instance was compiled with STAGE = want_stage
         a2.stage_shift = want_stage;
         return launch_kernel(kern, a2, threads, want_stage ? smem2 : smem, max_grid, st);
     }
-    if (!use_tma && want_stage && (F::N / (threads / F::S1)) % (1 << want_stage) == 0 && smem2 <= 227 * 1024) {
+    if (!use_tma && want_stage && (F::N / (threads / F::S1)) % 2 == 0 && smem2 <= 227 * 1024) {
         int occ0 = 0, occ = 0;
         FASTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
         FASTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
@@ -983,7 +980,7 @@ int launch_radix_instance(void (*kern)(RunArgs), const RunArgs& args, int thread
         FASTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ0, kern, threads, smem));
         FASTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem2));
         if (occ >= occ0 && occ >= 1) {
-            a2.stage_shift = want_stage;
+            a2.stage_shift = 1;
             smem = smem2;
         }
     }
