@@ -644,8 +644,8 @@ def run_ours(args):
     def e2e_step():
         sim._d['weight'].copy_(w_host, non_blocking=True)
         sim._d['U'].copy_(u_host, non_blocking=True)
-        res = sim.run()                        # fast/fast.py:115-140 contract: FastResult on the host
-        return res.power
+        sim.run()                              # fast/fast.py:115-140 contract: FastResult on the host,
+        return sim.I                           # sim.I = result.power (fast/fast.py:137), float64
 
     power = e2e_step()
     if world > 1:

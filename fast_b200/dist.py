@@ -23,22 +23,27 @@ def shard_range(total, rank, world):
 
 
 def gather_pairs(a, b, total, world):
-    """All-gather the per-rank result vectors into full-length ones (global pair order)."""
+    """All-gather the per-rank result vectors into full-length ones (global pair order): ONE collective over
+    equal-sized (padded) blocks, then the padding is dropped."""
     if world == 1:
         return a, b
     is_c = a.is_complex()
     if is_c:
         a, b = torch.view_as_real(a), torch.view_as_real(b)
-    width = a.shape[1:] if a.dim() > 1 else ()
+    width = tuple(a.shape[1:])
     longest = shard_range(total, 0, world)[1]
     loc = torch.zeros((2, longest, *width), dtype=a.dtype, device=a.device)
     loc[0, :a.shape[0]] = a
     loc[1, :b.shape[0]] = b
-    parts = [torch.empty_like(loc) for _ in range(world)]
-    td.all_gather(parts, loc)
+    everything = torch.empty((world, 2, longest, *width), dtype=a.dtype, device=a.device)
+    td.all_gather_into_tensor(everything.view(-1), loc.view(-1))
     sizes = [shard_range(total, r, world) for r in range(world)]
-    fa = torch.cat([parts[r][0, :hi - lo] for r, (lo, hi) in enumerate(sizes)])
-    fb = torch.cat([parts[r][1, :hi - lo] for r, (lo, hi) in enumerate(sizes)])
+    if all(hi - lo == longest for lo, hi in sizes):
+        fa = everything[:, 0].reshape(world * longest, *width)
+        fb = everything[:, 1].reshape(world * longest, *width)
+    else:
+        fa = torch.cat([everything[r, 0, :hi - lo] for r, (lo, hi) in enumerate(sizes)])
+        fb = torch.cat([everything[r, 1, :hi - lo] for r, (lo, hi) in enumerate(sizes)])
     if is_c:
         fa, fb = torch.view_as_complex(fa.contiguous()), torch.view_as_complex(fb.contiguous())
     return fa, fb

@@ -746,19 +746,14 @@ class Fast():
         return self.result
 
     def _to_host(self, flat):
-        """Device results -> the reference's host array (float64, complex128 when COHERENT) through a
-        pinned staging buffer that is reused across runs."""
-        src = torch.view_as_real(flat).reshape(-1) if flat.is_complex() else flat.reshape(-1)
-        n = src.numel()
-        buf = getattr(self, '_host_buf', None)
-        if buf is None or buf.numel() < n:
-            buf = self._host_buf = torch.empty(n, dtype=torch.float32, pin_memory=True)
-        buf[:n].copy_(src, non_blocking=True)
+        """Device results -> the reference's host array (float64, complex128 when COHERENT).  The widening
+        happens on the device and the copy lands in pinned memory from torch's caching host allocator; the
+        returned numpy array is a view of that block (no pass over the data on the host)."""
+        wide = torch.complex128 if flat.is_complex() else torch.float64
+        host = torch.empty(flat.shape, dtype=wide, pin_memory=True)
+        host.copy_(flat.to(wide), non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        host = buf[:n].numpy()
-        if flat.is_complex():
-            return host.view(numpy.complex64).astype(complex)
-        return host.astype(float)
+        return host.numpy()
 
     @_on_device
     def result_stats(self, db_lo=-60.0, db_hi=3.0, nbins=4096):

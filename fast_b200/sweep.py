@@ -75,7 +75,7 @@ def run_batch(sims, stats=None):
     out = []
     for e, sim in enumerate(sims):
         sim._d['result'] = flat[e]
-        sim.result = FastResult(host[e].copy(), sim.diffraction_limit)
+        sim.result = FastResult(host[e], sim.diffraction_limit)
         sim.I = sim.result.power
         out.append(sim.result)
     return out
