@@ -413,12 +413,7 @@ static int run_impl(const char* who, const FastbRunParams* p, const FastbRunBatc
     }
     if (p->n_pairs == 0) return FASTB_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    int impl = pick_impl(p);
-    if (impl == kImplBluestein && sh) {
-        // the sub-harmonic term is fused into the radix and direct kernels only
-        FASTB_REQUIRE(p->algo != FASTB_ALGO_BLUESTEIN, "%s: the chirp-z kernel has no sub-harmonic term", who);
-        impl = kImplDirect;
-    }
+    const int impl = pick_impl(p);
     const bool fast = (p->flags & FASTB_RUN_RNG_FAST) != 0;
     const int rng = d_noise ? kRngHost : (fast ? kRngFast : kRngPhilox);
     if (impl == kImplPair) {

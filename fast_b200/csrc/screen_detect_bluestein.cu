@@ -8,7 +8,8 @@
 // With G the (inverse-sign, unnormalised) line FFT:  y = conj(G(conj(G(a) G(b)))) / M,  a = x c.
 // G(b) / M and c are tabulated once per call in float64 (bluestein_tables_kernel).
 // Same pass structure, scratch layout, RNG contract and epilogue as the radix kernel
-// (screen_detect_kernel.cuh); replaces the O(N^2)-per-line direct kernel on the default path.
+// (screen_detect_kernel.cuh), including the fused sub-harmonic term; replaces the O(N^2)-per-line direct
+// kernel on the default path.
 #include "screen_detect_kernel.cuh"
 #include "bluestein.cuh"
 
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(256) bluestein_tables_kernel(int N, int M, int
 }
 
 
-template <int LOG2M, int RNG, int THREADS>
+template <int LOG2M, int RNG, bool SH, int THREADS>
 __global__ void __launch_bounds__(THREADS, THREADS <= 128 ? 4 : 2) screen_detect_bluestein(const __grid_constant__ RunArgs a,
                                                                       const float2* __restrict__ tables) {
     using F = LineFFT<LOG2M>;
@@ -86,6 +87,8 @@ __global__ void __launch_bounds__(THREADS, THREADS <= 128 ? 4 : 2) screen_detect
     float2* rows = chirp + N;                       // LPB x N staged inputs x[n] c[n]
     double* st = reinterpret_cast<double*>(rows + (size_t)LPB * N);
     float* red = reinterpret_cast<float*>(st + kStatWords);
+    float2* sh_amp = reinterpret_cast<float2*>(red + 4 * (THREADS / 32));     // SH only
+    float2* sh_tab = sh_amp + 28;
 
     const int tid = threadIdx.x;
     const int ln = tid / S1, u = tid % S1;
@@ -123,6 +126,7 @@ __global__ void __launch_bounds__(THREADS, THREADS <= 128 ? 4 : 2) screen_detect
         const uint32_t k0 = (uint32_t)id.seed, k1 = (uint32_t)(id.seed >> 32);
         const float* weight = a.weight + (size_t)id.item * N * N;
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        if (SH) sh_prepare(a, pair, id, sh_amp, sh_tab);       // table complete after the barriers of pass 1
 
         // ---- pass 1: LPB rows at a time
         for (int row0 = 0; row0 < N; row0 += LPB) {
@@ -185,12 +189,23 @@ __global__ void __launch_bounds__(THREADS, THREADS <= 128 ? 4 : 2) screen_detect
                 const float* ub = a.u_t + ((long long)c * P + kb);
                 // output sign (-1)^(row + column) = (-1)^(k + c + lo); k_off is even
                 const float sgn = ((F::k_base(u) + c + lo) & 1) ? -1.f : 1.f;
+                float2 ex[3];
+                if (SH) {
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) ex[i] = __ldg(a.sh_ex + i * P + c);
+                }
 #pragma unroll
                 for (int e = 0; e < 16; ++e)
                     if (need & (1u << e)) {
                         const int k = F::k_base(u) + F::k_off(e);
                         const float uu = __ldg(ub + F::k_off(e));
-                        accumulate(cmulf(v[e], chirp[k]), uu, uu * sgn, acc);
+                        const float2 phi = cmulf(v[e], chirp[k]);
+                        if (SH) {
+                            const float2 sp = sh_phase(sh_tab + (k - lo) * kShTab, ex);
+                            accumulate(make_float2(fmaf(sgn, phi.x, sp.x), fmaf(sgn, phi.y, sp.y)), uu, uu, acc);
+                        } else {
+                            accumulate(phi, uu, uu * sgn, acc);
+                        }
                     }
             }
         }
@@ -205,21 +220,25 @@ struct BlueCfg {
 };
 
 template <int LOG2M>
-size_t blue_smem_bytes(int n) {
+size_t blue_smem_bytes(int n, bool sh, int n_pup) {
     using F = LineFFT<LOG2M>;
     constexpr int T = BlueCfg<LOG2M>::kThreadsPerCta, LPB = T / F::S1;
     return sizeof(float2) * ((size_t)F::kTwA + F::kTwB + (size_t)LPB * F::kBuf + F::N + (size_t)n + (size_t)LPB * n) +
-           sizeof(double) * kStatWords + sizeof(float) * 4 * (T / 32);
+           sizeof(double) * kStatWords + sizeof(float) * 4 * (T / 32) + sh_smem_bytes(sh, n_pup);
 }
 
 template <int LOG2M>
 int launch_blue(const RunArgs& a, const RadixRequest& rq, const float2* tables, cudaStream_t st) {
     constexpr int T = BlueCfg<LOG2M>::kThreadsPerCta;
-    void (*kern)(RunArgs, const float2*) =
-        rq.rng == kRngHost   ? screen_detect_bluestein<LOG2M, kRngHost, T>
-        : rq.rng == kRngFast ? screen_detect_bluestein<LOG2M, kRngFast, T>
-                             : screen_detect_bluestein<LOG2M, kRngPhilox, T>;
-    const size_t smem = blue_smem_bytes<LOG2M>(a.n);
+    const bool sh = a.sh_weight != nullptr;
+    void (*kern)(RunArgs, const float2*) = nullptr;
+    if (sh) kern = rq.rng == kRngHost   ? screen_detect_bluestein<LOG2M, kRngHost, true, T>
+                   : rq.rng == kRngFast ? screen_detect_bluestein<LOG2M, kRngFast, true, T>
+                                        : screen_detect_bluestein<LOG2M, kRngPhilox, true, T>;
+    else kern = rq.rng == kRngHost   ? screen_detect_bluestein<LOG2M, kRngHost, false, T>
+                : rq.rng == kRngFast ? screen_detect_bluestein<LOG2M, kRngFast, false, T>
+                                     : screen_detect_bluestein<LOG2M, kRngPhilox, false, T>;
+    const size_t smem = blue_smem_bytes<LOG2M>(a.n, sh, a.n_pup);
     if (smem > 227 * 1024) {
         set_error("screen_detect_bluestein: N=%d needs %zu B of shared memory", a.n, smem);
         return FASTB_ERR_UNSUPPORTED;

@@ -458,6 +458,29 @@ def test_layer_screens_every_size_class_matches_oracle(fast, N):
     assert rel(got_rng, fo.layer_screens(dev_noise, W, df)) < 2e-5
 
 
+def test_chirp_z_path_carries_the_subharmonic_term(fast):
+    """SUBHARM on the auto-sized 164 x 164 grid: the chirp-z kernel (AUTO) with the fused 27-wave term
+    against the direct kernel, device RNG and host noise."""
+    g, p = load_golden('c1prime_subharm')
+    sim = fast.Fast(dict(p, NITER=12, NCHUNKS=2, SEED=41))
+    assert sim.subharmonics and sim.Npxls == 164
+    res = {}
+    for algo in (fast._lib.ALGO_AUTO, fast._lib.ALGO_BLUESTEIN, fast._lib.ALGO_DIRECT):
+        a, b = sim.screen_detect(0, 6, algo=algo)
+        res[algo] = torch.cat([a, b]).cpu().numpy()
+    np.testing.assert_array_equal(res[fast._lib.ALGO_AUTO], res[fast._lib.ALGO_BLUESTEIN])
+    np.testing.assert_allclose(res[fast._lib.ALGO_BLUESTEIN], res[fast._lib.ALGO_DIRECT], rtol=1e-4)
+    rng = np.random.default_rng(5)
+    noise = torch.from_numpy((rng.normal(size=(3, 164, 164)) + 1j * rng.normal(size=(3, 164, 164))).astype(np.complex64)).cuda()
+    lo = torch.from_numpy((rng.normal(size=(3, 27)) + 1j * rng.normal(size=(3, 27))).astype(np.complex64)).cuda()
+    chi = torch.zeros(sim.Niter, dtype=torch.float32, device='cuda')
+    out = {}
+    for algo in (fast._lib.ALGO_BLUESTEIN, fast._lib.ALGO_DIRECT):
+        a, b = sim.screen_detect(0, 3, noise=noise, noise_lo=lo, chi=chi, algo=algo)
+        out[algo] = torch.cat([a, b]).cpu().numpy()
+    np.testing.assert_allclose(out[fast._lib.ALGO_BLUESTEIN], out[fast._lib.ALGO_DIRECT], rtol=1e-4)
+
+
 # ---------------------------------------------------------------------------------------------
 # sub-harmonics (SUBHARM=True)
 # ---------------------------------------------------------------------------------------------
