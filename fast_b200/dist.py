@@ -136,6 +136,11 @@ def summarise(sums, minmax, hist, db_lo, db_hi):
     without the per-realisation array."""
     s = sums.cpu().numpy()
     n = s[0]
+    if n == 0:                       # nothing accumulated yet
+        nan = float('nan')
+        return {'n': 0, 'mean': nan, 'var': nan, 'scintillation_index': nan, 'mean_dB': nan, 'var_dB': nan,
+                'min': float(minmax[0]), 'max': float(minmax[1]), 'n_nonpositive': 0,
+                'hist': hist.cpu().numpy(), 'db_lo': db_lo, 'db_hi': db_hi}
     mean_r = s[1] / n
     var_r = s[2] / n - mean_r ** 2
     n_db = n - s[5]
