@@ -466,7 +466,10 @@ def per_workload(world, rank, flush, peak, dev):
             del sim
     # C3: 16 elevations x 1e4 realisations as ONE batched launch, (elevation x pair) sharded over the ranks
     ps = [configs.c3_elevation(e, niter=10000, nchunks=1, seed=100 + i) for i, e in enumerate(configs.C3_ELEVATIONS)]
+    t_build = time.perf_counter()
     sims = sweep.build_sims(ps)
+    torch.cuda.synchronize()
+    t_build = time.perf_counter() - t_build
     sweep.run_sweep(sims)                                  # warm-up
     torch.cuda.synchronize()
     if world > 1:
@@ -489,6 +492,7 @@ def per_workload(world, rank, flush, peak, dev):
               note="device time of sweep.run_sweep: stack weights, ONE K2 launch over 16 x 5000 pairs, statistics "
                    "all-gather, result all-gather, D2H; per-elevation mean dB_rel in mean_db", gpus=world)
         out['c3_sweep']['wall_ms'] = 1e3 * wall
+        out['c3_sweep']['build_ms_per_sample'] = 1e3 * t_build / len(sims)    # Fast(p): host scalars + K1 on the device
         out['c3_sweep']['mean_db'] = [round(float(r.dB_rel.mean()), 3) for r in res]
     # C5 as BASELINE.json states it: 1e6 realisations in total, strong-scaled over the ranks, one collective
     total = 1000000

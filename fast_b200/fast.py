@@ -32,6 +32,11 @@ logger = logging.getLogger(__name__)
 _AO_MODES = {'NOAO': _lib.AO_NOAO, 'AO': _lib.AO_AO, 'TT': _lib.AO_AO, 'LGSAO': _lib.AO_LGSAO}
 _RNG_MODES = ('device', 'device-fast', 'numpy')
 _GOLDEN64 = 0x9E3779B97F4A7C15
+# Aperture and fibre mode depend only on (N, dx, D, obscuration, W0 request, mode type): the samples of a pass
+# sweep (one Fast per elevation, fast/complete_orbit_simulation.py:217-228) share them, and the W0 optimisation
+# over N x N arrays is the bulk of the host-side construction time (10 ms at N = 256, 200 ms at N = 1024).
+_PUPIL_CACHE = {}
+_PUPIL_CACHE_MAX = 8
 
 
 def _on_device(method):
@@ -338,18 +343,26 @@ class Fast():
         N, dx = self.Npxls, self.dx
         self.dx_sat = self.D_sat / 32
         ptype = 'axicon' if self.params['AXICON'] else 'gauss'
-        pupil_full = funcs.compute_pupil(N, dx, self.D_ground, self.obsc_ground)
+        key = (int(N), float(dx), float(self.D_ground), float(self.obsc_ground), repr(self.W0), ptype)
+        hit = _PUPIL_CACHE.get(key)
+        if hit is None:
+            pupil_full = funcs.compute_pupil(N, dx, self.D_ground, self.obsc_ground)
+            mode_full, w0 = funcs.compute_gaussian_mode(pupil_full, dx, self.W0, D=self.D_ground,
+                                                        obsc=self.obsc_ground, ptype=ptype)
+            pupil_full.flags.writeable = mode_full.flags.writeable = False
+            if len(_PUPIL_CACHE) >= _PUPIL_CACHE_MAX:
+                _PUPIL_CACHE.pop(next(iter(_PUPIL_CACHE)))
+            hit = _PUPIL_CACHE[key] = (pupil_full, mode_full, w0)
+        pupil_full, mode_full, self.W0 = hit
         self.pupil_sat = funcs.compute_pupil(32, self.dx_sat, self.D_sat, self.obsc_sat)
-        mode_full, self.W0 = funcs.compute_gaussian_mode(pupil_full, dx, self.W0, D=self.D_ground,
-                                                         obsc=self.obsc_ground, ptype=ptype)
         self.pupil_mode_sat, self.W0_sat = funcs.compute_gaussian_mode(self.pupil_sat, self.dx_sat,
                                                                        "opt", ptype="gauss")
         self._pm_full = pupil_full * mode_full            # input of the device pupil filter
         lo, hi = (N - self.Npxls_pup) // 2, (N + self.Npxls_pup) // 2
         self._lo = lo
         self.pup_coords = numpy.array((numpy.arange(lo, hi), numpy.arange(lo, hi))).astype(int)
-        self.pupil = pupil_full[lo:hi, lo:hi]
-        self.pupil_mode = mode_full[lo:hi, lo:hi]
+        self.pupil = pupil_full[lo:hi, lo:hi].copy()          # own, writable crops (the full arrays are shared)
+        self.pupil_mode = mode_full[lo:hi, lo:hi].copy()
         if self.temporal:
             ft = self.freq.temporal
             self.pupil_filter_temporal = temporal.elongated_pupil_filter(self, ft.fx_axis, ft.fy_axis)
