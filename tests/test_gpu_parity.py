@@ -340,6 +340,22 @@ def test_prepared_tables_follow_weight_and_pupil_updates(fast):
     np.testing.assert_allclose(a3.cpu().numpy(), a0.cpu().numpy(), rtol=1e-6)
 
 
+def test_pupil_and_mode_are_shared_between_objects_but_not_aliased(fast):
+    """Aperture and fibre mode are cached per (N, dx, D, obscuration, W0 request, type): the samples of a sweep
+    share them; every object still owns writable crops, and a different request gets its own entry."""
+    g, p = load_golden('mini_ao')
+    a, b = fast.Fast(dict(p)), fast.Fast(dict(p, ZENITH_ANGLE=30.0))
+    np.testing.assert_array_equal(a.pupil, b.pupil)
+    np.testing.assert_array_equal(a.pupil_mode, b.pupil_mode)
+    assert a.W0 == b.W0 == pytest.approx(float(g['W0']), rel=1e-9)
+    a.pupil[0, 0] = 7.0                                   # writable, and private to `a`
+    assert b.pupil[0, 0] != 7.0 and fast.Fast(dict(p)).pupil[0, 0] != 7.0
+    c = fast.Fast(dict(p, W0=0.2))
+    assert c.W0 == 0.2 and not np.array_equal(c.pupil_mode, b.pupil_mode)
+    d = fast.Fast(dict(p, OBSC_GROUND=0.2))
+    assert d.pupil.sum() != b.pupil.sum()
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
 def test_device_key_is_honoured_when_another_device_is_current(fast):
     g, p = load_golden('mini_ao')
