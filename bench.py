@@ -65,12 +65,11 @@ def measured_peak():
 
 
 def kernel_digest():
-    """sha256 over the K2 device sources: the ncu-derived counters in profiles/ are only used when they
-    were captured from exactly these sources."""
+    """sha256 over the sources that define the K2 radix kernels (device code, FFT, RNG, instance selection): the
+    ncu-derived counters in profiles/ are only used when they were captured from exactly these sources."""
     h = hashlib.sha256()
     d = os.path.join(ROOT, 'fast_b200', 'csrc')
-    for f in ('fastb_common.cuh', 'fft_core.cuh', 'screen_detect_kernel.cuh', 'screen_detect_radix.cu',
-              'screen_detect_bluestein.cu', 'screen_detect.cu'):
+    for f in ('fastb_common.cuh', 'fft_core.cuh', 'screen_detect_kernel.cuh', 'screen_detect_radix.cu'):
         with open(os.path.join(d, f), 'rb') as fh:
             h.update(fh.read())
     return h.hexdigest()[:16]

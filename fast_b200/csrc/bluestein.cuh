@@ -13,6 +13,8 @@ int bluestein_log2m(int n, int n_out);                       // smallest M = 2^l
 size_t bluestein_table_bytes(int n, int n_out);
 // tables for outputs k in [lo, lo + n_out) of an n-point transform, float64 arithmetic
 int bluestein_prepare(int n, int n_out, int lo, void* tables, cudaStream_t st);
+// complex weight copies of the K2 chirp-z kernel: wc = weight * c[col] * c[row], n_items stacked tables
+int bluestein_prepare_weights(int n, int n_items, const float* weight, void* wc, cudaStream_t st);
 
 __device__ __forceinline__ float2 cmulf(float2 a, float2 b) {
     return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
@@ -24,20 +26,26 @@ template <class F, class Sync>
 __device__ __forceinline__ void chirp_convolve(int u, float2 (&v)[16], const typename F::Tw* twa,
                                                const typename F::Tw* twb, float2* buf, const float2* bhat,
                                                Sync sync) {
-    F::run(u, v, twa, twb, buf, sync);
+    // ONE copy of the line FFT in the instruction stream, executed twice (the kernels that inline this are
+    // instruction-cache bound otherwise: ncu `no_instruction` stalls of 1.0 per issue with two copies per pass)
+#pragma unroll 1
+    for (int rep = 0; rep < 2; ++rep) {
+        F::run(u, v, twa, twb, buf, sync);
+        if (rep == 0) {
 #pragma unroll
-    for (int e = 0; e < 16; ++e) {
-        const int k = F::k_base(u) + F::k_off(e);
-        const float2 z = cmulf(v[e], bhat[k]);
-        buf[k] = make_float2(z.x, -z.y);                  // conj(A B), natural order
+            for (int e = 0; e < 16; ++e) {
+                const int k = F::k_base(u) + F::k_off(e);
+                const float2 z = cmul(v[e], bhat[k]);
+                buf[k] = make_float2(z.x, -z.y);              // conj(A B), natural order
+            }
+            sync();
+#pragma unroll
+            for (int m = 0; m < 16; ++m) v[m] = buf[u + F::S1 * m];
+            sync();
+        }
     }
-    sync();
 #pragma unroll
-    for (int m = 0; m < 16; ++m) v[m] = buf[u + F::S1 * m];
-    sync();
-    F::run(u, v, twa, twb, buf, sync);
-#pragma unroll
-    for (int e = 0; e < 16; ++e) v[e].y = -v[e].y;        // y = conj(G(.)); the 1/M sits in bhat
+    for (int e = 0; e < 16; ++e) v[e].y = -v[e].y;            // y = conj(G(.)); the 1/M sits in bhat
 }
 
 }  // namespace fastb

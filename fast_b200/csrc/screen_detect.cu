@@ -55,6 +55,7 @@ bool bluestein_ok(int n, int n_pup);
 int bluestein_ctas_per_sm(int n, int n_pup);
 size_t bluestein_table_bytes(int n, int n_pup);
 int bluestein_prepare(int n, int n_pup, int lo, void* tables, cudaStream_t st);
+int bluestein_prepare_weights(int n, int n_items, const float* weight, void* wc, cudaStream_t st);
 int launch_bluestein(const RunArgs& a, const RadixRequest& rq, const void* tables, cudaStream_t st);
 
 namespace {
@@ -282,7 +283,8 @@ struct Layout {
 Layout layout_of(const FastbRunParams* p, int n_items, int impl) {
     Layout l;
     l.u_bytes = align_up(sizeof(float) * (size_t)(p->n_pup + 1) * p->n_pup, 256);
-    l.tab_bytes = align_up(sizeof(float) * (size_t)p->n * p->n * (n_items > 1 ? n_items : 1), 256);
+    // radix: real pre-scaled copies; chirp-z: complex chirped copies followed by the chirp tables
+    l.tab_bytes = align_up(sizeof(float) * (impl == kImplBluestein ? 2 : 1) * (size_t)p->n * p->n * (n_items > 1 ? n_items : 1), 256);
     if (impl == kImplBluestein) l.tab_bytes += align_up(bluestein_table_bytes(p->n, p->n_pup), 256);
     l.slot_bytes = (size_t)p->n * (p->n_pup + 1) * sizeof(float2);
     return l;
@@ -367,7 +369,8 @@ static int prepare_tables(const FastbRunParams* p, int n_items, int impl, const 
     if (impl == kImplRadix && d_weight)
         return prepare_weight_s(p->n, n_items, d_weight, (float*)tab, st);
     if (impl == kImplBluestein) {
-        const size_t w_bytes = align_up(sizeof(float) * (size_t)p->n * p->n * n_items, 256);
+        const size_t w_bytes = align_up(2 * sizeof(float) * (size_t)p->n * p->n * n_items, 256);
+        if ((rc = bluestein_prepare_weights(p->n, n_items, d_weight, tab, st))) return rc;
         return bluestein_prepare(p->n, p->n_pup, p->lo, tab + w_bytes, st);
     }
     return FASTB_OK;
@@ -475,7 +478,8 @@ static int run_impl(const char* who, const FastbRunParams* p, const FastbRunBatc
     const bool prepared = (p->flags & FASTB_RUN_PREPARED) != 0 && impl != kImplPair;
     if (!prepared) {
         // the radix launcher fills weight_s itself only when the device RNG needs it
-        rc = prepare_tables(p, n_items, impl, (impl == kImplRadix && rng != kRngHost) ? d_weight : nullptr, d_U,
+        rc = prepare_tables(p, n_items, impl,
+                            (impl == kImplBluestein || (impl == kImplRadix && rng != kRngHost)) ? d_weight : nullptr, d_U,
                             d_workspace, l, st);
         if (rc) return rc;
     }
@@ -487,7 +491,7 @@ static int run_impl(const char* who, const FastbRunParams* p, const FastbRunBatc
         case kImplPair: return launch_pair_n(ilog2(p->n), a, rq, st);
         case kImplRadix: return launch_radix_n(ilog2(p->n), a, rq, st);
         case kImplBluestein: {
-            const size_t w_bytes = align_up(sizeof(float) * (size_t)p->n * p->n * n_items, 256);
+            const size_t w_bytes = align_up(2 * sizeof(float) * (size_t)p->n * p->n * n_items, 256);
             return launch_bluestein(a, rq, (const char*)d_workspace + l.u_bytes + w_bytes, st);
         }
         default: break;

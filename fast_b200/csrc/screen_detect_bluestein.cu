@@ -7,9 +7,10 @@
 // d = k - n in (lo - N, lo + n_pup): N + n_pup - 1 consecutive values, alias-free on a circle of length M.
 // With G the (inverse-sign, unnormalised) line FFT:  y = conj(G(conj(G(a) G(b)))) / M,  a = x c.
 // G(b) / M and c are tabulated once per call in float64 (bluestein_tables_kernel).
-// Same pass structure, scratch layout, RNG contract and epilogue as the radix kernel
-// (screen_detect_kernel.cuh), including the fused sub-harmonic term; replaces the O(N^2)-per-line direct
-// kernel on the default path.
+// The input chirps of both passes are folded into a complex copy of the weight table (chirp_weight_kernel), every
+// line generates and colours its own row (no CTA-wide barrier inside a pass).  Same scratch layout, RNG contract
+// and epilogue as the radix kernel (screen_detect_kernel.cuh), including the fused sub-harmonic term; replaces
+// the O(N^2)-per-line direct kernel on the default path.
 #include "screen_detect_kernel.cuh"
 #include "bluestein.cuh"
 
@@ -69,6 +70,19 @@ __global__ void __launch_bounds__(256) bluestein_tables_kernel(int N, int M, int
 }
 
 
+// wc[item][r][j] = weight[item][r][j] * c[j] * c[r]: the input chirp of pass 1 (c[j]) and, because both passes are
+// linear, the input chirp of pass 2 (c[r'], constant along a row) folded into one complex table, so that colouring a
+// noise sample is a single complex multiply and pass 2 reads its inputs ready-made.  Phase in float64.
+__global__ void chirp_weight_kernel(const float* __restrict__ w, float2* __restrict__ wc, int N, long long total) {
+    const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= total) return;
+    const long long j = o % N, r = (o / N) % N;
+    double s, c;
+    sincospi((double)((j * j + r * r) % (2LL * N)) / (double)N, &s, &c);
+    const float x = w[o];
+    wc[o] = make_float2(x * (float)c, x * (float)s);
+}
+
 template <int LOG2M, int RNG, bool SH, int THREADS>
 __global__ void __launch_bounds__(THREADS, THREADS <= 128 ? 4 : 2) screen_detect_bluestein(const __grid_constant__ RunArgs a,
                                                                       const float2* __restrict__ tables) {
@@ -84,15 +98,14 @@ __global__ void __launch_bounds__(THREADS, THREADS <= 128 ? 4 : 2) screen_detect
     float2* bufs = reinterpret_cast<float2*>(twb + F::kTwB);
     float2* bhat = bufs + LPB * F::kBuf;            // M
     float2* chirp = bhat + M;                       // N
-    float2* rows = chirp + N;                       // LPB x N staged inputs x[n] c[n]
-    double* st = reinterpret_cast<double*>(rows + (size_t)LPB * N);
+    double* st = reinterpret_cast<double*>(chirp + N + (N & 1));
     float* red = reinterpret_cast<float*>(st + kStatWords);
     float2* sh_amp = reinterpret_cast<float2*>(red + 4 * (THREADS / 32));     // SH only
     float2* sh_tab = sh_amp + 28;
 
     const int tid = threadIdx.x;
     const int ln = tid / S1, u = tid % S1;
-    float2* buf = bufs + ln * F::kBuf;
+    float2* buf = bufs + ln * F::kBuf;              // the line's exchange buffer; also stages its input row
     const LineSync<S1> sync{ln};
 
     for (int j = tid; j < F::kTwA + F::kTwB; j += THREADS) {
@@ -107,7 +120,8 @@ __global__ void __launch_bounds__(THREADS, THREADS <= 128 ? 4 : 2) screen_detect
     __syncthreads();
 
     float2* T = a.scratch + (size_t)blockIdx.x * N * P;
-    const int S = (N + 15) / 16;                    // noise blocks per row (include/fastb.h)
+    const int S = (N + 15) / 16;                    // noise blocks per row (include/fastb.h); S <= S1 because M >= N
+    const int n1 = (N + LPB - 1) / LPB, n2 = (P + LPB - 1) / LPB;
 
     // wanted outputs of this thread: k = k_base + k_off(e) inside [lo, lo + P)
     const int kb = F::k_base(u) - lo;
@@ -116,92 +130,90 @@ __global__ void __launch_bounds__(THREADS, THREADS <= 128 ? 4 : 2) screen_detect
     for (int e = 0; e < 16; ++e)
         if ((unsigned)(kb + F::k_off(e)) < (unsigned)P) need |= 1u << e;
 
-    // chirp-z of the line held as v[m] = a[u + S1 m] (a = x c, zero beyond N): on return v[e] holds
-    // sum_n a[n] conj(c[k - n]) for k = k_out(u, e), valid where `need` says so
-    auto convolve = [&](float2 (&v)[16]) { chirp_convolve<F>(u, v, twa, twb, buf, bhat, sync); };
-
     for (long long pair = blockIdx.x; pair < a.n_pairs; pair += gridDim.x) {
         const PairId id = pair_id(a, pair);
         const unsigned long long g = id.g;
         const uint32_t k0 = (uint32_t)id.seed, k1 = (uint32_t)(id.seed >> 32);
-        const float* weight = a.weight + (size_t)id.item * N * N;
+        const float2* wc = reinterpret_cast<const float2*>(a.weight_s) + (size_t)id.item * N * N;
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        if (SH) sh_prepare(a, pair, id, sh_amp, sh_tab);       // table complete after the barriers of pass 1
+        if (SH) sh_prepare(a, pair, id, sh_amp, sh_tab);       // complete after the barrier between the passes
 
-        // ---- pass 1: LPB rows at a time
-        for (int row0 = 0; row0 < N; row0 += LPB) {
-            const int nr = min(LPB, N - row0);
-            __syncthreads();                                   // the previous group's lines are loaded
-            if (RNG != kRngHost) {
-                for (int idx = tid; idx < nr * S; idx += THREADS) {
-                    const int rl = idx / S, t = idx % S, r = row0 + rl;
-                    uint32_t mr[16], ma[16];
-                    if (RNG == kRngFast) noise_block_fields_fast((uint32_t)(r * S + t), g, k0, k1, mr, ma);
-                    else noise_block_fields((uint32_t)(r * S + t), g, k0, k1, mr, ma);
+        // One loop body serves both passes (instruction-cache footprint): iterations [0, n1) are rows, [n1, n1 + n2)
+        // kept columns.  Pass 1: every line makes its own row (no CTA-wide barrier inside a pass): thread u < S owns
+        // noise block u of the row, colours its 16 cells with one complex multiply each and drops them into the line
+        // buffer in natural order; the line then picks them up in the FFT's input layout.  Idle lines run on zeros
+        // (warps stay converged).  Pass 2: T already carries the input chirp c[r'].
+        for (int it = 0; it < n1 + n2; ++it) {
+            const bool rows = it < n1;
+            if (it == n1) __syncthreads();                     // every row of T is stored before a column is read
+            const int line = (rows ? it : it - n1) * LPB + ln; // r' or c
+            const bool live = line < (rows ? N : P);
+            float2 v[16];
+            if (rows) {
+                if (live && u < S) {
+                    // the 16 complex weights first: their L2 latency hides behind the Philox rounds
+                    const float2* wrow = wc + (size_t)line * N + u;
+                    float2 wv[16];
 #pragma unroll
-                    for (int m = 0; m < 16; ++m) {
-                        const int j = t + S * m;
-                        if (j < N)
-                            rows[rl * N + j] = cmulf(weighted_normal_m(mr[m], ma[m], __ldg(weight + (size_t)r * N + j)), chirp[j]);
+                    for (int m = 0; m < 16; ++m) wv[m] = (u + S * m < N) ? __ldg(wrow + S * m) : make_float2(0.f, 0.f);
+                    if (RNG != kRngHost) {
+                        uint32_t mr[16], ma[16];
+                        if (RNG == kRngFast) noise_block_fields_fast((uint32_t)(line * S + u), g, k0, k1, mr, ma);
+                        else noise_block_fields((uint32_t)(line * S + u), g, k0, k1, mr, ma);
+#pragma unroll
+                        for (int m = 0; m < 16; ++m) {
+                            const int j = u + S * m;
+                            if (j < N) buf[j] = cmul(weighted_normal_m(mr[m], ma[m], 1.0f), wv[m]);
+                        }
+                    } else {
+                        const float2* nrow = a.noise + ((size_t)pair * N + line) * N;
+#pragma unroll
+                        for (int m = 0; m < 16; ++m) {
+                            const int j = u + S * m;
+                            if (j < N) buf[j] = cmul(__ldg(nrow + j), wv[m]);
+                        }
                     }
                 }
+                sync();
+#pragma unroll
+                for (int m = 0; m < 16; ++m) {
+                    const int n = u + S1 * m;
+                    v[m] = (live && n < N) ? buf[n] : make_float2(0.f, 0.f);
+                }
+                sync();                                        // phase A of the transform rewrites the buffer
             } else {
-                for (int idx = tid; idx < nr * N; idx += THREADS) {
-                    const int rl = idx / N, j = idx % N, r = row0 + rl;
-                    const float2 nz = a.noise[((size_t)pair * N + r) * N + j];
-                    const float w0 = weight[(size_t)r * N + j];
-                    rows[rl * N + j] = cmulf(make_float2(nz.x * w0, nz.y * w0), chirp[j]);
+                const float2* tcol = T + (size_t)(live ? line : 0) * N;
+#pragma unroll
+                for (int m = 0; m < 16; ++m) {
+                    const int n = u + S1 * m;
+                    v[m] = (live && n < N) ? __ldcg(tcol + n) : make_float2(0.f, 0.f);
                 }
             }
-            __syncthreads();
-            // every line runs (idle ones on zeros) so that warps stay converged
-            const int r = row0 + ln;
-            float2 v[16];
-#pragma unroll
-            for (int m = 0; m < 16; ++m) {
-                const int n = u + S1 * m;
-                v[m] = (n < N && r < N) ? rows[ln * N + n] : make_float2(0.f, 0.f);
-            }
-            convolve(v);
-            if (r < N) {
+
+            chirp_convolve<F>(u, v, twa, twb, buf, bhat, sync);
+
+            if (!live) continue;
+            if (rows) {
+                float2* tb = T + ((long long)kb * N + line);
 #pragma unroll
                 for (int e = 0; e < 16; ++e)
-                    if (need & (1u << e)) {
-                        const int k = F::k_base(u) + F::k_off(e);
-                        __stcg(T + ((long long)(k - lo) * N + r), cmulf(v[e], chirp[k]));
-                    }
-            }
-        }
-        __syncthreads();                                       // every row of T is stored
-
-        // ---- pass 2: LPB kept columns at a time
-        for (int col0 = 0; col0 < P; col0 += LPB) {
-            const int c = col0 + ln;
-            float2 v[16];
-            const float2* tcol = T + (size_t)(c < P ? c : 0) * N;
-#pragma unroll
-            for (int m = 0; m < 16; ++m) {
-                const int n = u + S1 * m;
-                v[m] = (n < N && c < P) ? cmulf(__ldcg(tcol + n), chirp[n]) : make_float2(0.f, 0.f);
-            }
-            convolve(v);
-            if (c < P) {
-                const float* ub = a.u_t + ((long long)c * P + kb);
+                    if (need & (1u << e)) __stcg(tb + (long long)F::k_off(e) * N, cmul(v[e], chirp[kb + lo + F::k_off(e)]));
+            } else {
+                const float* ub = a.u_t + ((long long)line * P + kb);
                 // output sign (-1)^(row + column) = (-1)^(k + c + lo); k_off is even
-                const float sgn = ((F::k_base(u) + c + lo) & 1) ? -1.f : 1.f;
+                const float sgn = ((F::k_base(u) + line + lo) & 1) ? -1.f : 1.f;
                 float2 ex[3];
                 if (SH) {
 #pragma unroll
-                    for (int i = 0; i < 3; ++i) ex[i] = __ldg(a.sh_ex + i * P + c);
+                    for (int i = 0; i < 3; ++i) ex[i] = __ldg(a.sh_ex + i * P + line);
                 }
 #pragma unroll
                 for (int e = 0; e < 16; ++e)
                     if (need & (1u << e)) {
-                        const int k = F::k_base(u) + F::k_off(e);
                         const float uu = __ldg(ub + F::k_off(e));
-                        const float2 phi = cmulf(v[e], chirp[k]);
+                        const float2 phi = cmul(v[e], chirp[kb + lo + F::k_off(e)]);
                         if (SH) {
-                            const float2 sp = sh_phase(sh_tab + (k - lo) * kShTab, ex);
+                            const float2 sp = sh_phase(sh_tab + (kb + F::k_off(e)) * kShTab, ex);
                             accumulate(make_float2(fmaf(sgn, phi.x, sp.x), fmaf(sgn, phi.y, sp.y)), uu, uu, acc);
                         } else {
                             accumulate(phi, uu, uu * sgn, acc);
@@ -223,7 +235,7 @@ template <int LOG2M>
 size_t blue_smem_bytes(int n, bool sh, int n_pup) {
     using F = LineFFT<LOG2M>;
     constexpr int T = BlueCfg<LOG2M>::kThreadsPerCta, LPB = T / F::S1;
-    return sizeof(float2) * ((size_t)F::kTwA + F::kTwB + (size_t)LPB * F::kBuf + F::N + (size_t)n + (size_t)LPB * n) +
+    return sizeof(float2) * ((size_t)F::kTwA + F::kTwB + (size_t)LPB * F::kBuf + F::N + (size_t)n + (n & 1)) +
            sizeof(double) * kStatWords + sizeof(float) * 4 * (T / 32) + sh_smem_bytes(sh, n_pup);
 }
 
@@ -271,6 +283,12 @@ int bluestein_ctas_per_sm(int n, int n_pup) { return blue_log2m(n, n_pup) <= 8 ?
 
 size_t bluestein_table_bytes(int n, int n_pup) {
     return sizeof(float2) * ((size_t)n + ((size_t)1 << blue_log2m(n, n_pup)));
+}
+
+int bluestein_prepare_weights(int n, int n_items, const float* weight, void* wc, cudaStream_t st) {
+    const long long total = (long long)n * n * n_items;
+    chirp_weight_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(weight, (float2*)wc, n, total);
+    return check_launch("chirp_weight_kernel");
 }
 
 int bluestein_prepare(int n, int n_pup, int lo, void* tables, cudaStream_t st) {
