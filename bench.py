@@ -64,12 +64,21 @@ def measured_peak():
     return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
-def kernel_digest():
-    """sha256 over the sources that define the K2 radix kernels (device code, FFT, RNG, instance selection): the
-    ncu-derived counters in profiles/ are only used when they were captured from exactly these sources."""
+_DIGEST_FILES = {
+    # the sources that define the K2 radix kernels (device code, FFT, RNG, instance selection) ...
+    'radix': ('fastb_common.cuh', 'fft_core.cuh', 'screen_detect_kernel.cuh', 'screen_detect_radix.cu'),
+    # ... and the chirp-z kernel (C1')
+    'bluestein': ('fastb_common.cuh', 'fft_core.cuh', 'screen_detect_kernel.cuh', 'bluestein.cuh',
+                  'screen_detect_bluestein.cu'),
+}
+
+
+def kernel_digest(kind='radix'):
+    """sha256 over the sources of one K2 kernel family: the ncu-derived counters in profiles/ are only used when
+    they were captured from exactly these sources."""
     h = hashlib.sha256()
     d = os.path.join(ROOT, 'fast_b200', 'csrc')
-    for f in ('fastb_common.cuh', 'fft_core.cuh', 'screen_detect_kernel.cuh', 'screen_detect_radix.cu'):
+    for f in _DIGEST_FILES[kind]:
         with open(os.path.join(d, f), 'rb') as fh:
             h.update(fh.read())
     return h.hexdigest()[:16]
@@ -87,8 +96,9 @@ def ncu_counters(workload):
     w = rec.get('workloads', {}).get(workload)
     if not w:
         return None, 'no ncu capture for this workload'
-    if rec.get('kernel_digest') != kernel_digest():
-        return None, f"ncu capture is of other kernel sources ({rec.get('kernel_digest')}): not used"
+    kind = 'bluestein' if workload == 'c1prime' else 'radix'
+    if rec.get('kernel_digests', {}).get(kind) != kernel_digest(kind):
+        return None, f"ncu capture is of other kernel sources ({rec.get('kernel_digests', {}).get(kind)}): not used"
     return w, 'ncu --set full capture of these sources (profiles/kernel_counters_r02.json)'
 
 

@@ -55,7 +55,7 @@ def ncu_csv(rep, *args):
 def raw_counters(rep):
     rows = ncu_csv(rep, '--page', 'raw')
     hdr, units = rows[0], rows[1]
-    row = [r for r in rows[2:] if 'screen_detect' in ' '.join(r[:12])][0]
+    row = [r for r in rows[2:] if 'screen_detect' in ' '.join(r[:12])][-1]
     return {h: (u, v) for h, u, v in zip(hdr, units, row)}
 
 
@@ -232,7 +232,7 @@ def main(tag, rnd):
     import bench
     rec = {'_comment': 'per-pair counters of the K2 launch captured by ncu --set full (one launch = the timed step of '
                        'bench.py --workload <w>); used by bench.py only while kernel_digest matches the tree',
-           'kernel_digest': bench.kernel_digest(), 'workloads': {}}
+           'kernel_digests': {k: bench.kernel_digest(k) for k in ('radix', 'bluestein')}, 'workloads': {}}
     for w, pairs in PAIRS.items():
         rep = os.path.join(ROOT, 'gpurun_out', f'prof_{w}_{tag}.ncu-rep')
         if not os.path.exists(rep):
