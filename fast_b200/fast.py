@@ -763,6 +763,8 @@ class Fast():
         happens on the device and the copy lands in pinned memory from torch's caching host allocator; the
         returned numpy array is a view of that block (no pass over the data on the host)."""
         wide = torch.complex128 if flat.is_complex() else torch.float64
+        if flat.numel() < 65536:                   # short runs (e.g. TEMPORAL chunks): a pinned block is not worth it
+            return flat.to(wide).cpu().numpy()
         host = torch.empty(flat.shape, dtype=wide, pin_memory=True)
         host.copy_(flat.to(wide), non_blocking=True)
         torch.cuda.current_stream().synchronize()
