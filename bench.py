@@ -467,11 +467,11 @@ def per_workload(world, rank, flush, peak, dev):
             sb = dist.StatsBuffers(4096, dev)
             ms = timed_launches(sim, n_real, 3, flush, sb)
             entry(name, n_real, ms, sim.Npxls, bool(p['COHERENT']), kern)
-            if name == 'c2':
-                simf = fast_b200.Fast(dict(p, RNG='device-fast'))
-                msf = timed_launches(simf, n_real, 3, flush, sb)
-                entry('c2_device_fast', n_real, msf, sim.Npxls, False, kern + ', RNG device-fast',
-                      note="opt-in RNG='device-fast' (Philox4x32-7, 40 bits per complex sample)")
+            simf = fast_b200.Fast(dict(p, RNG='device-fast'))
+            msf = timed_launches(simf, n_real, 3, flush, sb)
+            entry(name + '_device_fast', n_real, msf, sim.Npxls, bool(p['COHERENT']), kern + ', RNG device-fast',
+                  note="opt-in RNG='device-fast' (Philox4x32-7, 40 bits per complex sample)")
+            del simf
             del sim
     # C3: 16 elevations x 1e4 realisations as ONE batched launch, (elevation x pair) sharded over the ranks
     ps = [configs.c3_elevation(e, niter=10000, nchunks=1, seed=100 + i) for i, e in enumerate(configs.C3_ELEVATIONS)]

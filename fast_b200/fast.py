@@ -753,8 +753,7 @@ class Fast():
             flat = torch.cat(parts)
             self._d.pop('noise', None)
         self._d['result'] = flat
-        self.result = FastResult(self._to_host(flat), self.diffraction_limit)
-        self.I = self.result.power
+        self._publish(flat)
         logger.info(self.result)
         return self.result
 
@@ -763,12 +762,23 @@ class Fast():
         happens on the device and the copy lands in pinned memory from torch's caching host allocator; the
         returned numpy array is a view of that block (no pass over the data on the host)."""
         wide = torch.complex128 if flat.is_complex() else torch.float64
+        if flat.dtype != wide:
+            flat = flat.to(wide)
         if flat.numel() < 65536:                   # short runs (e.g. TEMPORAL chunks): a pinned block is not worth it
-            return flat.to(wide).cpu().numpy()
+            return flat.cpu().numpy()
         host = torch.empty(flat.shape, dtype=wide, pin_memory=True)
-        host.copy_(flat.to(wide), non_blocking=True)
+        host.copy_(flat, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return host.numpy()
+
+    def _publish(self, flat):
+        """self.result / self.I from the device results (fast/fast.py:136-137).  `I = result.power` is the
+        IEEE product diffraction_limit * r: formed on the device in float64 (bit-identical to numpy's) so that
+        the host makes no pass over NITER values."""
+        wide = flat.to(torch.complex128 if flat.is_complex() else torch.float64)
+        self.result = FastResult(self._to_host(wide), self.diffraction_limit)
+        self.I = self._to_host(wide * self.diffraction_limit)
+        return self.result
 
     @_on_device
     def result_stats(self, db_lo=-60.0, db_hi=3.0, nbins=4096):

@@ -77,6 +77,7 @@ def test_run_with_reference_noise_matches_reference(fast, name):
         assert worst_rel_per_item(res._r, want) < RTOL_R
     np.testing.assert_allclose(sim.logamp, g['logamp'], rtol=1e-12)
     assert np.isfinite(sim.I).all()
+    np.testing.assert_array_equal(sim.I, res.power)          # I = result.power (fast/fast.py:137), formed on the device
 
 
 def test_c2_4000_realisations_match_reference(fast):
@@ -542,6 +543,7 @@ def test_elevation_sweep_matches_individual_runs(fast, rng):
     assert fast._lib.launch_count() - n0 == 3        # transpose-U, weight pre-scale, ONE K2 launch
     res2 = [r._r.copy() for r in sweep.run_sweep(sims)]
     for p, r, r2, sim in zip(ps, res, res2, sims):
+        np.testing.assert_array_equal(sim.I, sim.result.power)
         solo_sim = fast.Fast(dict(p))
         np.testing.assert_array_equal(r._r, solo_sim.run()._r)
         np.testing.assert_array_equal(r2, solo_sim.run()._r)
