@@ -21,6 +21,8 @@ ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
 COMMON = ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']
 # per-file extra flags: the PSD kernel follows numpy's operation order (no FMA contraction)
 _DBG = ['-DFASTB_TUNE_DBG'] if os.environ.get('FASTB_TUNE_DBG') else []
+if os.environ.get('FASTB_SPLIT'):              # tuning builds: FASTB_SPLIT=0 -> LineFFT for N >= 512
+    _DBG += ['-DFASTB_SPLIT=' + os.environ['FASTB_SPLIT']]
 if os.environ.get('FASTB_SCALAR_STAGES'):      # tuning builds: which FFT stages use scalar FP32 (fft_core.cuh)
     _DBG += ['-DFASTB_SCALAR_STAGES=' + os.environ['FASTB_SCALAR_STAGES']]
 # object name -> (source, extra flags).  The radix kernels of K2 are compiled once per grid size
@@ -55,6 +57,7 @@ def _digest():
     h.update(os.environ.get('FASTB_TUNE', '').encode())
     h.update(os.environ.get('FASTB_TUNE_DBG', '').encode())
     h.update(os.environ.get('FASTB_SCALAR_STAGES', '').encode())
+    h.update(os.environ.get('FASTB_SPLIT', '').encode())
     return h.hexdigest()
 
 

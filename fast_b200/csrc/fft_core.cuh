@@ -532,6 +532,99 @@ FASTB_HD constexpr unsigned keep_mask(int half) {
     return m;
 }
 
+// Line FFT for N = 512, 1024, 2048 as R = N/256 interleaved 256-point transforms ("split first"):
+//   stage 0  thread u holds x[u + S1 m]; the R elements n' + 256 q (q < R) of one residue n' < 256 sit in the
+//            same thread, so the radix-R step over the TOP digit of n is done in registers:
+//            Y_p[n'] = w_N^(n' p) sum_q x[n' + 256 q] w_R^(q p),   and   X[R k' + p] = DFT256(Y_p)[k'].
+//            The R sequences are exchanged once through the line buffer (natural order, one region per p).
+//   then     the 16 threads u = 16 p + t' run the 256-point transform of sequence p exactly as LineFFT<8> does
+//            (16 x 16, one exchange inside the half-warp): register a2 of thread (p, t') holds k' = t' + 16 a2.
+// Output k = R t' + p + 16 R a2: the register index is the TOP digit of k, so a centred crop window keeps only
+// 6 (N = 512) / 4 (N = 1024) of the 16 outputs of the LAST 16-point DFT -- the compile-time pruning removes
+// more than with the a + 16 (a2 + 16 b2) order of LineFFT -- and there is one twiddle pass less; the only
+// line-wide synchronisations are the two around the first exchange.  TUNING FLAVOUR (FASTB_SPLIT=1): measured
+// 5 - 8 % slower than LineFFT on B200 (profiles/experiments_r02.txt, 12): it executes fewer instructions but
+// moves 1.5x the data through shared memory.
+template <int LOG2N>
+struct LineFFTSplit {
+    using Value = float2;
+    using Tw = float2;
+    using Sub = LineFFT<8, float2>;
+    static constexpr int N = 1 << LOG2N;
+    static constexpr int E = 16;
+    static constexpr int kLines = 1;
+    static constexpr int S1 = N / 16;                       // threads per line
+    static constexpr int R = N / 256;                       // interleaved sub-transforms: 2, 4, 8
+    static constexpr int kML = 16 / R;                      // radix-R steps per thread
+    static_assert(LOG2N >= 9 && LOG2N <= 11, "split flavour serves N = 512, 1024, 2048");
+    static constexpr int kRegion = Sub::kBuf;               // float2 per sub-transform (>= 256, padded)
+    static constexpr int kBuf = R * kRegion;
+    static constexpr int kTwRow = 18;                       // 16 used; 144-byte rows
+    static constexpr int kTwA = Sub::kTwA;                  // w_256^(t a) = w_N^(R t a)
+    static constexpr int kTwB = kTwRow * S1;                // stage-0 twiddles: row u, entry m_lo R + p
+    static constexpr bool kShflC = false;
+    template <unsigned KEEP, typename Sync>
+    FASTB_HD static void run_shfl(int, float2 (&)[16], const float2*, const float2*, float2*, Sync) {}
+
+    FASTB_HD static int n_in(int t, int m) { return t + S1 * m; }
+    FASTB_HD static int twa_exponent(int idx) {
+        const int t = idx / Sub::kTwRow, a = idx % Sub::kTwRow;
+        return a < 16 ? (R * t * a) & (N - 1) : 0;
+    }
+    FASTB_HD static int twb_exponent(int idx) {
+        const int u = idx / kTwRow, c = idx % kTwRow;
+        return c < 16 ? ((u + 16 * R * (c / R)) * (c % R)) & (N - 1) : 0;
+    }
+
+    // radix-R step over q (register m = m_lo + kML q), twiddle, store sequence p at region p in natural order
+    FASTB_HD static void stage0(int u, float2 (&v)[16], const float2* twb, float2* buf) {
+        const float2* row = twb + u * kTwRow;
+#pragma unroll
+        for (int ml = 0; ml < kML; ++ml) {
+            float2 y[R];
+#pragma unroll
+            for (int q = 0; q < R; ++q) y[q] = v[ml + kML * q];
+            if constexpr (R == 2) dft2(y[0], y[1]);
+            else if constexpr (R == 4) dft4(y[0], y[1], y[2], y[3]);
+            else dft8(y);
+            const int np = u + 16 * R * ml;
+#pragma unroll
+            for (int p = 0; p < R; ++p) {
+                const float2 z = p == 0 ? y[0] : cmul(y[p], row[ml * R + p]);
+                buf[p * kRegion + np] = z;
+            }
+        }
+    }
+    // thread u = 16 p + t' picks up sequence p in the 256-point transform's input layout
+    FASTB_HD static void gather0(int u, float2 (&v)[16], const float2* buf) {
+        const float2* reg = buf + (u / 16) * kRegion + (u % 16);
+#pragma unroll
+        for (int m = 0; m < 16; ++m) v[m] = reg[16 * m];
+    }
+
+    template <typename Sync>
+    FASTB_HD static void run(int u, float2 (&v)[16], const float2* twa, const float2* twb, float2* buf, Sync sync) {
+        stage0(u, v, twb, buf);
+        sync();
+        gather0(u, v, buf);
+        float2* reg = buf + (u / 16) * kRegion;
+#if defined(__CUDA_ARCH__)
+        __syncwarp();           // region p is read and rewritten by the same 16 lanes
+#endif
+        Sub::phase_a(u % 16, v, twa, reg);
+#if defined(__CUDA_ARCH__)
+        __syncwarp();
+#endif
+        Sub::phase_b(u % 16, v, nullptr, reg);
+        sync();                 // the next line's stage 0 rewrites every region
+    }
+
+    FASTB_HD static constexpr int k_base(int u) { return R * (u % 16) + u / 16; }
+    FASTB_HD static constexpr int k_off(int e) { return 16 * R * e; }
+    FASTB_HD static constexpr int k_out(int u, int e) { return k_base(u) + k_off(e); }
+    FASTB_HD static constexpr bool k_off_all_even() { return true; }
+};
+
 // Line FFT with 32 complex elements per thread for N = 512 (32 x 16) and N = 1024 (32 x 32):
 // S1 = N/32 threads per line, ONE shared-memory exchange per line (tuning flavour, one line).
 //   phase A  thread t holds x[t + S1 m], m < 32: 32-point DFT over m -> a = k mod 32, twiddle

@@ -386,9 +386,23 @@ struct LineSync {
 // same throughput in every CTA shape.
 template <int LOG2N, int E>
 struct RadixCfg;
+// FASTB_SPLIT=1 (tuning builds): N >= 512 uses the split-first line FFT (fft_core.cuh, LineFFTSplit) instead of
+// LineFFT with its shuffle / shared-memory last stage.  Measured slower (C4 -8 %, C5 -5 %: fewer FFT instructions,
+// but 16 more shared-memory stores and 8 more loads per line and thread on an L1 data pipe that is already 71 % busy)
+#ifndef FASTB_SPLIT
+#define FASTB_SPLIT 0
+#endif
+template <int LOG2N, bool SPLIT = (FASTB_SPLIT != 0 && LOG2N >= 9)>
+struct RadixFft {
+    using type = LineFFT<LOG2N>;
+};
+template <int LOG2N>
+struct RadixFft<LOG2N, true> {
+    using type = LineFFTSplit<LOG2N>;
+};
 template <int LOG2N>
 struct RadixCfg<LOG2N, 16> {
-    using F = LineFFT<LOG2N>;
+    using F = typename RadixFft<LOG2N>::type;
     static constexpr int kThreadsPerCta = LOG2N <= 8 ? 128 : 512;
     static constexpr int kMinBlocks = LOG2N <= 8 ? 4 : 1;
 };

@@ -22,9 +22,10 @@ constexpr int T = Cfg::kThreadsPerCta, M = Cfg::kMinBlocks;
 constexpr int kStage = kLog2N <= 9 ? 1 : 0;
 static_assert((F::N / (T / F::S1)) % 2 == 0, "row iterations come in pairs");
 
-// last FFT stage on warp shuffles where it measured faster: the radix-2 stage of N = 512 (+5.4 %); the
-// radix-4 stage of N = 1024 is 0.5 - 1 % slower than the shared-memory exchange (profiles/experiments_r02.txt)
-constexpr bool kShuffle = F::S2 == 2;
+// LineFFT flavour only (FASTB_SPLIT=0): last FFT stage on warp shuffles where it measured faster, the radix-2
+// stage of N = 512 (+5.4 %); the radix-4 stage of N = 1024 is 0.5 - 1 % slower than the shared-memory exchange
+// (profiles/experiments_r02.txt).  The split-first flavour has no such stage.
+constexpr bool kShuffle = F::kShflC && F::S1 == 32;
 
 template <int RNG, bool SH, int WIN>
 constexpr auto kern() { return screen_detect_radix<F, RNG, SH, T, M, 0, WIN, kShuffle, false, kStage>; }

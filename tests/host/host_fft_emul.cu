@@ -143,6 +143,46 @@ double run_32(unsigned seed) {
     return check(x, X, seen, 1, label);
 }
 
+// the split-first flavour (N = 512, 1024, 2048): stage 0 of every thread, then the 256-point transforms
+template <int LOG2N>
+double run_split(unsigned seed) {
+    using F = LineFFTSplit<LOG2N>;
+    constexpr int N = F::N;
+    std::vector<float2> x[2], X[2];
+    std::vector<int> seen(N, 0);
+    srand(seed);
+    x[0].resize(N);
+    X[0].resize(N);
+    for (int i = 0; i < N; ++i)
+        x[0][i] = make_float2((float)rand() / RAND_MAX - 0.5f, (float)rand() / RAND_MAX - 0.5f);
+    std::vector<float2> twa = table<float2>(F::kTwA, N, F::twa_exponent), twb = table<float2>(F::kTwB, N, F::twb_exponent);
+    std::vector<float2> buf(F::kBuf);
+    std::vector<float2> keep((size_t)16 * F::S1);
+    float2 v[16];
+    for (int u = 0; u < F::S1; ++u) {
+        for (int m = 0; m < 16; ++m) v[m] = x[0][F::n_in(u, m)];
+        F::stage0(u, v, twb.data(), buf.data());
+    }
+    for (int u = 0; u < F::S1; ++u) {                       // all gathers before any phase-A store (same regions)
+        F::gather0(u, v, buf.data());
+        for (int e = 0; e < 16; ++e) keep[u * 16 + e] = v[e];
+    }
+    for (int u = 0; u < F::S1; ++u) {
+        for (int e = 0; e < 16; ++e) v[e] = keep[u * 16 + e];
+        F::Sub::phase_a(u % 16, v, twa.data(), buf.data() + (u / 16) * F::kRegion);
+    }
+    for (int u = 0; u < F::S1; ++u) {
+        F::Sub::phase_b(u % 16, v, nullptr, buf.data() + (u / 16) * F::kRegion);
+        for (int e = 0; e < 16; ++e) {
+            X[0][F::k_out(u, e)] = v[e];
+            seen[F::k_out(u, e)]++;
+        }
+    }
+    char label[96];
+    snprintf(label, sizeof label, "N=%d split R=%d S1=%d buf=%d", N, F::R, F::S1, F::kBuf);
+    return check(x, X, seen, 1, label);
+}
+
 // keep_mask<F>(half) (compile-time output pruning) against a brute-force scan of k_out, and the
 // register counts DESIGN.md quotes for the bench crops
 template <int LOG2N>
@@ -193,6 +233,13 @@ int main() {
     w = fmax(w, run_one<11, pc>(16));
     w = fmax(w, run_32<9>(7));
     w = fmax(w, run_32<10>(8));
+    w = fmax(w, run_split<9>(21));
+    w = fmax(w, run_split<10>(22));
+    w = fmax(w, run_split<11>(23));
+    // the split flavour keeps fewer registers for the bench crops: C4 6 of 16 (as before), C5 4 of 16, and the
+    // kept ones are whole outputs of the last 16-point DFT
+    if (__builtin_popcount(keep_mask<LineFFTSplit<9>>(96)) != 6) return 3;
+    if (__builtin_popcount(keep_mask<LineFFTSplit<10>>(128)) != 4) return 3;
     printf("worst %.3e\n", w);
     return w < 2e-6 ? 0 : 1;
 }

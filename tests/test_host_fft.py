@@ -17,6 +17,6 @@ def test_line_fft_index_algebra(tmp_path):
                    check=True, capture_output=True)
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout
-    assert out.stdout.count('max_err') == 14
+    assert out.stdout.count('max_err') == 17
     # compile-time output pruning: keep_mask<F>() equals a brute-force scan for 6 sizes x 3 window classes
     assert out.stdout.count('keeps') == 18 and 'MISMATCH' not in out.stdout
