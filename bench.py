@@ -69,7 +69,7 @@ _DIGEST_FILES = {
     'radix': ('fastb_common.cuh', 'fft_core.cuh', 'screen_detect_kernel.cuh', 'screen_detect_radix.cu'),
     # ... and the chirp-z kernel (C1')
     'bluestein': ('fastb_common.cuh', 'fft_core.cuh', 'screen_detect_kernel.cuh', 'bluestein.cuh',
-                  'screen_detect_bluestein.cu'),
+                  'screen_detect_bluestein.cu', 'screen_detect_bluestein_m.cu'),
 }
 
 

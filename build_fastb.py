@@ -31,14 +31,18 @@ SOURCES = {
     'api': ('api.cu', []),
     'psd_build': ('psd_build.cu', ['-fmad=false']),
     'screen_detect': ('screen_detect.cu', ['-Xptxas', '-v'] + _DBG),
-    'screen_detect_bluestein': ('screen_detect_bluestein.cu', ['-Xptxas', '-v'] + _DBG),
+    'screen_detect_bluestein': ('screen_detect_bluestein.cu', []),
     'stats': ('stats.cu', []),
     'link_metrics': ('link_metrics.cu', ['-fmad=false']),
     'temporal': ('temporal.cu', []),
     'layer_screens_fft': ('layer_screens_fft.cu', ['-Xptxas', '-v']),
 }
+_BLUE = ['-DFASTB_BLUE_TWO=' + os.environ['FASTB_BLUE_TWO']] if os.environ.get('FASTB_BLUE_TWO') else []
 for _k in range(6, 12):
     SOURCES[f'screen_detect_radix_{_k}'] = ('screen_detect_radix.cu', ['-Xptxas', '-v', f'-DFASTB_LOG2N={_k}'] + _DBG)
+    # the chirp-z kernels likewise once per transform length M = 2^k
+    SOURCES[f'screen_detect_bluestein_{_k}'] = ('screen_detect_bluestein_m.cu',
+                                                ['-Xptxas', '-v', f'-DFASTB_LOG2M={_k}'] + _DBG + _BLUE)
 if os.environ.get('FASTB_TUNE'):
     # tuning builds only: env-driven alternative kernel shapes / variants (never part of the product)
     SOURCES['screen_detect_tune'] = (os.path.join('tune', 'screen_detect_tune.cu'), ['-Xptxas', '-v'] + _DBG)
@@ -58,6 +62,7 @@ def _digest():
     h.update(os.environ.get('FASTB_TUNE_DBG', '').encode())
     h.update(os.environ.get('FASTB_SCALAR_STAGES', '').encode())
     h.update(os.environ.get('FASTB_SPLIT', '').encode())
+    h.update(os.environ.get('FASTB_BLUE_TWO', '').encode())
     return h.hexdigest()
 
 

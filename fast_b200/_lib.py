@@ -122,6 +122,9 @@ _SIGS = {
                                  C.c_void_p, C.c_void_p]),
     'fastb_rng_dump_mode': (C.c_int, [C.c_uint64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int64,
                                       C.c_void_p, C.c_void_p]),
+    'fastb_noise_stride': (C.c_int32, [C.c_int32, C.c_int32]),
+    'fastb_rng_dump_stride': (C.c_int, [C.c_uint64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64,
+                                        C.c_int64, C.c_void_p, C.c_void_p]),
     'fastb_layer_screens_workspace_bytes': (C.c_int64, [C.c_int32, C.c_int32]),
     'fastb_layer_screens': (C.c_int, [C.c_int32, C.c_int32, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_int64, C.c_void_p]),
@@ -308,11 +311,22 @@ def screens_crop(rp: RunParams, weight, phs, workspace, noise=None, subharm=None
            'fastb_screens_crop')
 
 
-def rng_dump(seed, pair, n, device, chi_first=0, chi_count=0, want_tile=True, fast=False):
+def noise_stride(n, n_pup):
+    """Noise blocks per row of the K2 device RNG for an (n, n_pup) problem (include/fastb.h)."""
+    s = lib.fastb_noise_stride(int(n), int(n_pup))
+    if s < 1:
+        raise FastbError(f'fastb_noise_stride: bad geometry n={n}, n_pup={n_pup}')
+    return s
+
+
+def rng_dump(seed, pair, n, device, chi_first=0, chi_count=0, want_tile=True, fast=False, n_pup=None):
+    """Noise tile of one pair (and chi normals).  n_pup given: the K2 stride of that problem; otherwise
+    ceil(n / 16) (K2 for powers of two, K4 layer screens)."""
     tile = torch.empty((n, n, 2), dtype=torch.float32, device=device) if want_tile else None
     chi = torch.empty(chi_count, dtype=torch.float32, device=device) if chi_count else None
-    _check(lib.fastb_rng_dump_mode(int(seed), int(pair), n, int(bool(fast)), _ptr(tile), int(chi_first),
-                                   int(chi_count), _ptr(chi), _stream()), 'fastb_rng_dump_mode')
+    stride = noise_stride(n, n_pup) if n_pup is not None else (n + 15) // 16
+    _check(lib.fastb_rng_dump_stride(int(seed), int(pair), n, stride, int(bool(fast)), _ptr(tile), int(chi_first),
+                                     int(chi_count), _ptr(chi), _stream()), 'fastb_rng_dump_stride')
     return tile, chi
 
 

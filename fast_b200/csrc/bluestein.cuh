@@ -1,8 +1,9 @@
 // Chirp-z (Bluestein) building blocks shared by the K2 kernel for grids that are not a power of two
-// (screen_detect_bluestein.cu) and the TEMPORAL layer screens (layer_screens_fft.cu).
+// (screen_detect_bluestein.cu, screen_detect_bluestein_m.cu) and the TEMPORAL layer screens
+// (layer_screens_fft.cu).
 //   X[k] = c[k] sum_n (x[n] c[n]) conj(c[k - n]),  c[m] = e^{i pi m^2 / N}
 // The circular convolution of length M = 2^LOG2M runs on the register line FFT G (inverse sign,
-// unnormalised):  y = conj(G(conj(G(a) G(b)))) / M.  Tables (float2): chirp[N] then bhat[M] = G(b) / M.
+// unnormalised):  y = conj(G(conj(G(a) G(b)))) / M.
 #pragma once
 #include "fastb_common.cuh"
 #include "fft_core.cuh"
@@ -10,11 +11,37 @@
 namespace fastb {
 
 int bluestein_log2m(int n, int n_out);                       // smallest M = 2^l >= n + n_out - 1 (l >= 6)
+
+// ---- layer screens (full-size outputs): tables chirp[N] then bhat[M] = G(b) / M, natural order ----
 size_t bluestein_table_bytes(int n, int n_out);
 // tables for outputs k in [lo, lo + n_out) of an n-point transform, float64 arithmetic
 int bluestein_prepare(int n, int n_out, int lo, void* tables, cudaStream_t st);
-// complex weight copies of the K2 chirp-z kernel: wc = weight * c[col] * c[row], n_items stacked tables
-int bluestein_prepare_weights(int n, int n_items, const float* weight, void* wc, cudaStream_t st);
+
+// ---- K2: geometry of an (N, n_pup) problem on the length-M transform ------------------------------
+// S1 = M / 16 threads serve a line and thread u holds the inputs n = u + S1 m, m < 16.  Only the
+// MC = ceil(N / S1) first of them can be non-zero; the kernels are compiled per class C = cell PAIRS per
+// thread (5: up to 10 cells and any crop, 6, 7, 8: exactly 2C - 1 or 2C cells), which also bounds the
+// crop: n_pup <= M - N + 1 <= (18 - 2C) S1 for C > 5, so the second transform of the convolution is
+// pruned to the low output window at compile time.
+struct BlueGeom {
+    int log2m, M, S1, C;
+};
+BlueGeom blue_geom(int n, int n_pup);
+// complex chirped weight copies, one float4 per cell pair: entry (row r, pair j < C, thread u) at
+// (r C + j) S1 + u holds wc[r][u + S1 2j], wc[r][u + S1 (2j + 1)], wc = weight c[col] c[row] (0 beyond N)
+size_t bluestein_weight_bytes(int n, int n_pup, int n_items);
+// tables of the K2 kernel: bhat in the register order of the line FFT (S1 rows of 18 float2, 16 used:
+// row u, entry e = G(b')[k_out(u, e)] / M for the kernel shifted to the crop, b'[d] = conj(c[d + lo]))
+// followed by the output chirp c[lo + k'], k' < n_pup
+size_t bluestein_k2_table_bytes(int n, int n_pup);
+struct RunArgs;
+struct RadixRequest;
+bool bluestein_ok(int n, int n_pup);           // even N, not a radix size, N + n_pup - 1 <= 2048
+int bluestein_ctas_per_sm(int n, int n_pup);   // design occupancy (scratch sizing)
+// fills the K2 tables and, unless weight == NULL, the chirped weight copies of n_items stacked tables
+int bluestein_prepare_k2(int n, int n_pup, int lo, int n_items, const float* weight, void* wcq, void* tables,
+                         cudaStream_t st);
+int launch_bluestein(const RunArgs& a, const RadixRequest& rq, const void* tables, cudaStream_t st);
 
 __device__ __forceinline__ float2 cmulf(float2 a, float2 b) {
     return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));

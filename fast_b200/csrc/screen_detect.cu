@@ -3,6 +3,7 @@
 // size); general even N: screen_detect_bluestein.cu; this unit also holds the pruned direct-DFT
 // kernel (cross-check / inspection path) and the small table-preparation kernels.
 #include "screen_detect_kernel.cuh"
+#include "bluestein.cuh"
 
 namespace fastb {
 
@@ -51,12 +52,6 @@ int launch_pair_n(int log2n, const RunArgs& a, const RadixRequest& rq, cudaStrea
 int radix_ctas_per_sm(int log2n) { return log2n <= 8 ? 4 : 1; }
 
 // general even N through Bluestein's chirp-z on the radix line FFT (screen_detect_bluestein.cu)
-bool bluestein_ok(int n, int n_pup);
-int bluestein_ctas_per_sm(int n, int n_pup);
-size_t bluestein_table_bytes(int n, int n_pup);
-int bluestein_prepare(int n, int n_pup, int lo, void* tables, cudaStream_t st);
-int bluestein_prepare_weights(int n, int n_items, const float* weight, void* wc, cudaStream_t st);
-int launch_bluestein(const RunArgs& a, const RadixRequest& rq, const void* tables, cudaStream_t st);
 
 namespace {
 
@@ -92,7 +87,7 @@ __global__ void __launch_bounds__(kThreads) screen_detect_direct(const __grid_co
         for (int row0 = 0; row0 < N; row0 += R) {
             const int nr = min(R, N - row0);
             if (RNG != kRngHost) {
-                const int S = (N + 15) / 16;
+                const int S = a.noise_stride;
                 for (int idx = tid; idx < nr * S; idx += kThreads) {
                     const int rl = idx / S, t = idx % S, r = row0 + rl;
                     uint32_t mr[16], ma[16];
@@ -206,10 +201,9 @@ __global__ void pair_u_kernel(const float* __restrict__ U, int P, float* __restr
     u_p[i] = c < P ? U[(size_t)r * P + c] : 0.f;
 }
 
-__global__ void rng_dump_kernel(unsigned long long seed, unsigned long long g, int N, int fast, float2* tile,
+__global__ void rng_dump_kernel(unsigned long long seed, unsigned long long g, int N, int S, int fast, float2* tile,
                                 long long chi_first, long long chi_count, float* chi) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int S = (N + 15) / 16;
     if (tile && i < (long long)N * S) {
         const int r = (int)(i / S), t = (int)(i % S);
         uint32_t mr[16], ma[16];
@@ -234,6 +228,12 @@ size_t direct_smem_bytes(int n, bool sh, int n_pup) {
 }
 
 bool radix_ok(int n) { return n >= 64 && n <= 2048 && (n & (n - 1)) == 0; }
+// noise blocks per row of the device RNG (include/fastb.h): the threads per line of the transform that owns the grid
+int noise_stride(int n, int n_pup) {
+    if (radix_ok(n)) return n / 16;
+    if (bluestein_ok(n, n_pup)) return blue_geom(n, n_pup).S1;
+    return (n + 15) / 16;
+}
 int ilog2(int n) {
     int l = 0;
     while ((1 << l) < n) ++l;
@@ -284,8 +284,11 @@ Layout layout_of(const FastbRunParams* p, int n_items, int impl) {
     Layout l;
     l.u_bytes = align_up(sizeof(float) * (size_t)(p->n_pup + 1) * p->n_pup, 256);
     // radix: real pre-scaled copies; chirp-z: complex chirped copies followed by the chirp tables
-    l.tab_bytes = align_up(sizeof(float) * (impl == kImplBluestein ? 2 : 1) * (size_t)p->n * p->n * (n_items > 1 ? n_items : 1), 256);
-    if (impl == kImplBluestein) l.tab_bytes += align_up(bluestein_table_bytes(p->n, p->n_pup), 256);
+    if (impl == kImplBluestein)
+        l.tab_bytes = align_up(bluestein_weight_bytes(p->n, p->n_pup, n_items), 256) +
+                      align_up(bluestein_k2_table_bytes(p->n, p->n_pup), 256);
+    else
+        l.tab_bytes = align_up(sizeof(float) * (size_t)p->n * p->n * (n_items > 1 ? n_items : 1), 256);
     l.slot_bytes = (size_t)p->n * (p->n_pup + 1) * sizeof(float2);
     return l;
 }
@@ -318,7 +321,8 @@ static int validate_run(const FastbRunParams* p, const char* who) {
         return FASTB_ERR_UNSUPPORTED;
     }
     if (p->algo == FASTB_ALGO_BLUESTEIN && !bluestein_ok(p->n, p->n_pup)) {
-        set_error("%s: chirp-z path needs n + n_pup - 1 <= 2048, got n=%d n_pup=%d", who, p->n, p->n_pup);
+        set_error("%s: chirp-z path serves grids other than the powers of two 64..2048 with n + n_pup - 1 <= 2048, "
+                  "got n=%d n_pup=%d", who, p->n, p->n_pup);
         return FASTB_ERR_UNSUPPORTED;
     }
     if (p->n > 4096) {
@@ -369,9 +373,8 @@ static int prepare_tables(const FastbRunParams* p, int n_items, int impl, const 
     if (impl == kImplRadix && d_weight)
         return prepare_weight_s(p->n, n_items, d_weight, (float*)tab, st);
     if (impl == kImplBluestein) {
-        const size_t w_bytes = align_up(2 * sizeof(float) * (size_t)p->n * p->n * n_items, 256);
-        if ((rc = bluestein_prepare_weights(p->n, n_items, d_weight, tab, st))) return rc;
-        return bluestein_prepare(p->n, p->n_pup, p->lo, tab + w_bytes, st);
+        const size_t w_bytes = align_up(bluestein_weight_bytes(p->n, p->n_pup, n_items), 256);
+        return bluestein_prepare_k2(p->n, p->n_pup, p->lo, n_items, d_weight, tab, tab + w_bytes, st);
     }
     return FASTB_OK;
 }
@@ -449,6 +452,7 @@ static int run_impl(const char* who, const FastbRunParams* p, const FastbRunBatc
     a.out_b = d_out_b;
     a.scratch = (float2*)((char*)d_workspace + l.scratch_off());
     a.rows_per_block = direct_rows(p->n);
+    a.noise_stride = noise_stride(p->n, p->n_pup);
     a.n_items = n_items;
     a.ppi = batch ? batch->pairs_per_item : 0;
     a.item_sigma = batch ? batch->d_sigma_chi : nullptr;
@@ -491,7 +495,7 @@ static int run_impl(const char* who, const FastbRunParams* p, const FastbRunBatc
         case kImplPair: return launch_pair_n(ilog2(p->n), a, rq, st);
         case kImplRadix: return launch_radix_n(ilog2(p->n), a, rq, st);
         case kImplBluestein: {
-            const size_t w_bytes = align_up(2 * sizeof(float) * (size_t)p->n * p->n * n_items, 256);
+            const size_t w_bytes = align_up(bluestein_weight_bytes(p->n, p->n_pup, n_items), 256);
             return launch_bluestein(a, rq, (const char*)d_workspace + l.u_bytes + w_bytes, st);
         }
         default: break;
@@ -522,13 +526,27 @@ extern "C" int fastb_rng_dump(uint64_t seed, int64_t pair, int32_t n, float* d_n
 
 extern "C" int fastb_rng_dump_mode(uint64_t seed, int64_t pair, int32_t n, int32_t fast, float* d_noise_tile,
                                      int64_t chi_first, int64_t chi_count, float* d_chi_normals, void* stream) {
+    return fastb_rng_dump_stride(seed, pair, n, (n + 15) / 16, fast, d_noise_tile, chi_first, chi_count, d_chi_normals,
+                                 stream);
+}
+
+extern "C" int32_t fastb_noise_stride(int32_t n, int32_t n_pup) {
+    if (n < 2 || (n % 2) || n_pup < 1 || n_pup > n) return -1;
+    return noise_stride(n, n_pup);
+}
+
+extern "C" int fastb_rng_dump_stride(uint64_t seed, int64_t pair, int32_t n, int32_t stride, int32_t fast,
+                                     float* d_noise_tile, int64_t chi_first, int64_t chi_count, float* d_chi_normals,
+                                     void* stream) {
     FASTB_REQUIRE(n >= 2 && (n % 2) == 0, "fastb_rng_dump: n must be even");
+    FASTB_REQUIRE(stride >= 1 && (long long)stride * 16 >= n, "fastb_rng_dump: 16 stride must cover n");
     FASTB_REQUIRE(pair >= 0 && chi_first >= 0 && chi_count >= 0, "fastb_rng_dump: negative index");
-    long long work = d_noise_tile ? (long long)n * ((n + 15) / 16) : 0;
+    long long work = d_noise_tile ? (long long)n * stride : 0;
     if (d_chi_normals && chi_count > work) work = chi_count;
     if (work == 0) return FASTB_OK;
     rng_dump_kernel<<<(unsigned)((work + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        seed, (unsigned long long)pair, n, fast ? 1 : 0, (float2*)d_noise_tile, chi_first, chi_count, d_chi_normals);
+        seed, (unsigned long long)pair, n, stride, fast ? 1 : 0, (float2*)d_noise_tile, chi_first, chi_count,
+        d_chi_normals);
     return check_launch("rng_dump_kernel");
 }
 
@@ -555,6 +573,7 @@ extern "C" int fastb_screens_crop(const FastbRunParams* p, const float* d_weight
     a.noise = (const float2*)d_noise;
     a.scratch = (float2*)((char*)d_workspace + l.scratch_off());
     a.rows_per_block = direct_rows(p->n);
+    a.noise_stride = noise_stride(p->n, p->n_pup);
     a.n_items = 1;
     a.phs = d_phs;
     if (sh) {

@@ -40,6 +40,7 @@ struct RunArgs {
     float* out_b;
     float2* scratch;          // gridDim.x slots of n*n_pup float2
     int rows_per_block;       // direct kernel only
+    int noise_stride;         // direct kernel: noise blocks per row S of the device RNG (include/fastb.h)
     int stage_shift;          // radix kernel: 1 = stage two rows per line slot before storing, 0 = store directly
     // batch of configurations sharing the grid and U (FastbRunBatch): flattened pair index
     // q = item * ppi + g;  n_items <= 1: a single configuration, q = g

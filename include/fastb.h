@@ -152,7 +152,13 @@ int64_t fastb_pupil_filter_workspace_bytes(int32_t n);
  * chi is indexed by that global index.
  *
  * Device RNG (d_noise == NULL): Philox4x32-10, key = (seed lo, seed hi).  Noise block
- * b = r*S + t, S = ceil(N/16), holds the 16 cells (r, t + S m), m < 16.  It is fed by six calls
+ * b = r*S + t holds the 16 cells (r, t + S m), m < 16 (cells beyond the grid are not used).  The noise
+ * stride S = fastb_noise_stride(N, n_pup) is the number of threads that serve a line in the kernel that
+ * owns the grid, so that a thread's noise block is its transform input:
+ *   N = 64..2048 power of two                          S = N / 16
+ *   other even N with N + n_pup - 1 <= 2048 (chirp-z)   S = M / 16, M = 2^ceil(log2(N + n_pup - 1)) >= 64
+ *   anything else (direct DFT)                         S = ceil(N / 16)
+ * and does not depend on the FASTB_ALGO_* requested.  A block is fed by six calls
  * q < 6 with counter (b, g lo, g hi, 0x5CE7E000 + q): 24 words W[4q+j].  Word triple G < 8
  * (W[3G], W[3G+1], W[3G+2]) gives four 23-bit fields -- the top 23 bits of each word and one
  * field mixed from their low 9 bits -- so 24 words feed 16 Box-Muller pairs:
@@ -177,10 +183,11 @@ enum {
     FASTB_ALGO_RADIX_PAIR = 3,      /* same FFT on two adjacent lines per thread group, all arithmetic
                                        in packed FP32 (FADD2/FMUL2/FFMA2): fewer instructions, but
                                        measured slower than RADIX on B200; kept as a cross-check */
-    FASTB_ALGO_BLUESTEIN = 4        /* any even N with N + n_pup - 1 <= 2048: chirp-z (Bluestein) on the
-                                       radix line FFT of length M = 2^ceil(log2(N + n_pup - 1)); what AUTO
-                                       selects for grids that are not a power of two (the reference's
-                                       NPXLS 'auto' sizes, fast/fast.py:166-187, e.g. 164) */
+    FASTB_ALGO_BLUESTEIN = 4        /* any even N with N + n_pup - 1 <= 2048 that is not a RADIX size: chirp-z
+                                       (Bluestein) on the radix line FFT of length
+                                       M = 2^ceil(log2(N + n_pup - 1)); what AUTO selects for grids that are not
+                                       a power of two (the reference's NPXLS 'auto' sizes,
+                                       fast/fast.py:166-187, e.g. 164) */
 };
 
 /* FastbRunParams.flags */
@@ -295,9 +302,17 @@ int fastb_screens_crop(const FastbRunParams* p, const float* d_weight, const flo
  * and the chi normals of realisations [first, first+count).  Either output may be NULL. */
 int fastb_rng_dump(uint64_t seed, int64_t pair, int32_t n, float* d_noise_tile,
                    int64_t chi_first, int64_t chi_count, float* d_chi_normals, void* stream);
-/* same with the noise stream selected: rng_fast = 0 default stream, 1 'device-fast' */
+/* same with the noise stream selected: rng_fast = 0 default stream, 1 'device-fast'.  Both use the
+ * stride ceil(n / 16), which is the K2 stride for powers of two and the stride of the K4 layer screens. */
 int fastb_rng_dump_mode(uint64_t seed, int64_t pair, int32_t n, int32_t rng_fast, float* d_noise_tile,
                         int64_t chi_first, int64_t chi_count, float* d_chi_normals, void* stream);
+/* noise stride S of the K2 device RNG for an (n, n_pup) problem (see the K2 contract above); -1 for
+ * arguments fastb_screen_detect would reject */
+int32_t fastb_noise_stride(int32_t n, int32_t n_pup);
+/* the tile for an explicit stride (16 stride >= n) */
+int fastb_rng_dump_stride(uint64_t seed, int64_t pair, int32_t n, int32_t stride, int32_t rng_fast,
+                          float* d_noise_tile, int64_t chi_first, int64_t chi_count, float* d_chi_normals,
+                          void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * K4: TEMPORAL (frozen-flow) mode -- Fast.compute_phs_temporal (fast/fast.py:607-637).

@@ -615,12 +615,27 @@ def _bm_fields(mr, ma):
     return r * np.cos(t) + 1j * r * np.sin(t)
 
 
-def device_noise_pair_fast(seed, pair, N):
+def noise_stride(N, n_pup=None):
+    """Noise blocks per row S of the K2 device RNG (include/fastb.h, "Device RNG"): N / 16 for the
+    radix sizes (powers of two 64..2048); M / 16 with M = 2^ceil(log2(N + n_pup - 1)) >= 64 for the
+    other even N with N + n_pup - 1 <= 2048 (the chirp-z kernel); ceil(N / 16) otherwise, and when
+    n_pup is not given (the K4 layer screens)."""
+    if n_pup is None or (64 <= N <= 2048 and N & (N - 1) == 0):
+        return (N + 15) // 16
+    if N % 2 == 0 and N >= 4 and N + n_pup - 1 <= 2048:
+        M = 64
+        while M < N + n_pup - 1:
+            M *= 2
+        return M // 16
+    return (N + 15) // 16
+
+
+def device_noise_pair_fast(seed, pair, N, S=None):
     """The 'device-fast' stream (include/fastb.h, FASTB_RUN_RNG_FAST): same block / cell mapping,
     five Philox4x32-7 calls q with counter (b, pair lo, pair hi, STREAM_NOISE_FAST + q) give 20
     words; cell m owns word W[m] and byte m % 4 of the extra word W[16 + m // 4]:
     radius field = W[m] & 0x7FFFFF, angle field = ((W[m] >> 9) & 0x7FC000) ^ (byte << 8)."""
-    S = (N + 15) // 16
+    S = (N + 15) // 16 if S is None else S
     b = (np.arange(N, dtype=np.uint64)[:, None] * np.uint64(S) + np.arange(S, dtype=np.uint64)[None, :])
     W = []
     for q in range(5):
@@ -638,15 +653,16 @@ def device_noise_pair_fast(seed, pair, N):
     return out[:, :N]
 
 
-def device_noise_pair(seed, pair, N, fast=False):
+def device_noise_pair(seed, pair, N, fast=False, S=None):
     """The complex white-noise tile the CUDA generator produces for global pair index `pair`
-    (contract: include/fastb.h).  Noise block b = r*S + t, S = ceil(N/16), holds cells
-    (r, t + S m), m < 16; six Philox calls q with counter (b, pair lo, pair hi, STREAM_NOISE + q)
-    give 24 words; each word triple feeds two Box-Muller pairs (top 23 bits of each word, plus
-    one field mixed from the three low 9-bit remainders)."""
+    (contract: include/fastb.h).  Noise block b = r*S + t holds cells (r, t + S m), m < 16 (those
+    beyond the grid are dropped), S = noise_stride(N, n_pup) (default ceil(N/16)); six Philox calls q
+    with counter (b, pair lo, pair hi, STREAM_NOISE + q) give 24 words; each word triple feeds two
+    Box-Muller pairs (top 23 bits of each word, plus one field mixed from the three low 9-bit
+    remainders)."""
     if fast:
-        return device_noise_pair_fast(seed, pair, N)
-    S = (N + 15) // 16
+        return device_noise_pair_fast(seed, pair, N, S)
+    S = (N + 15) // 16 if S is None else S
     b = (np.arange(N, dtype=np.uint64)[:, None] * np.uint64(S) + np.arange(S, dtype=np.uint64)[None, :])
     W = []
     for q in range(6):
@@ -693,7 +709,8 @@ def run_mc_device_rng(init, seed, n_pairs, pairs_per_chunk, coherent=None, fast=
         i_im = i_re + pairs_per_chunk
         # noise_of(g): the tile dumped from the device (fastb_rng_dump) instead of the restatement,
         # which removes the ~1e-6 MUFU difference of the noise itself from the comparison
-        noise = (noise_of(g) if noise_of is not None else device_noise_pair(seed, g, N, fast))[None]
+        noise = (noise_of(g) if noise_of is not None
+                 else device_noise_pair(seed, g, N, fast, noise_stride(N, init['Npup'])))[None]
         phs = screens_from_noise(noise, init['powerspec'], init['df'], init['lo'], init['hi'])
         r = detector(phs, U, chi_all[[i_re, i_im]], coherent)
         out[i_re], out[i_im] = r[0], r[1]
@@ -956,7 +973,8 @@ def run_mc_device_rng_subharm(init, seed, n_pairs, pairs_per_chunk):
         chunk, pp = divmod(g, pairs_per_chunk)
         i_re = chunk * 2 * pairs_per_chunk + pp
         i_im = i_re + pairs_per_chunk
-        phs = screens_from_noise(device_noise_pair(seed, g, N)[None], init['powerspec'], init['df'], lo, hi)
+        phs = screens_from_noise(device_noise_pair(seed, g, N, S=noise_stride(N, init['Npup']))[None], init['powerspec'],
+                                 init['df'], lo, hi)
         phs = phs + subharm_screens(device_subharm_noise(seed, g)[None], W_sh, axes, N, dx)[:, lo:hi, :][:, :, lo:hi]
         r = detector(phs, U, chi_all[[i_re, i_im]], coherent)
         out[i_re], out[i_im] = r[0], r[1]

@@ -116,6 +116,21 @@ def test_fast_stream_noise_matches_restatement(fast, N):
     assert err.max() < 3e-4 and np.sqrt((err ** 2).mean()) < 2e-6
 
 
+@pytest.mark.parametrize('N,P,S', [(164, 82, 16), (100, 30, 16), (300, 180, 32), (20, 20, 4), (1000, 200, 128),
+                                   (256, 82, 16), (2100, 100, 132)])
+@pytest.mark.parametrize('is_fast', [False, True])
+def test_noise_stride_follows_the_kernel_that_owns_the_grid(fast, N, P, S, is_fast):
+    """include/fastb.h: S = N/16 (radix sizes), M/16 (chirp-z sizes), ceil(N/16) (direct DFT) -- and the
+    tile generated with that stride is the restated one."""
+    assert fast._lib.noise_stride(N, P) == S == fo.noise_stride(N, P)
+    if N > 1000:
+        return
+    tile, _ = fast._lib.rng_dump(seed=99, pair=(1 << 32) + 3, n=N, device='cuda', fast=is_fast, n_pup=P)
+    want = fo.device_noise_pair(99, (1 << 32) + 3, N, fast=is_fast, S=S)
+    err = np.abs(torch.view_as_complex(tile).cpu().numpy() - want)
+    assert err.max() < 3e-4 and np.sqrt((err ** 2).mean()) < 2e-6
+
+
 @pytest.mark.parametrize('rng', ['device', 'device-fast'])
 @pytest.mark.parametrize('name,npairs', [('mini_ao', 10), ('mini_coherent', 10), ('c2', 3), ('c1prime', 3),
                                          ('c4', 2), ('c5', 2)])
@@ -133,7 +148,7 @@ def test_device_rng_run_matches_oracle(fast, name, npairs, rng):
     N, is_fast = init['N'], rng == 'device-fast'
 
     def dumped(gp):
-        tile, _ = fast._lib.rng_dump(seed=77, pair=gp, n=N, device='cuda', fast=is_fast)
+        tile, _ = fast._lib.rng_dump(seed=77, pair=gp, n=N, device='cuda', fast=is_fast, n_pup=init['Npup'])
         return torch.view_as_complex(tile).cpu().numpy().astype(complex)
     want = fo.run_mc_device_rng(init, 77, 2 * npairs, niter // nch // 2, noise_of=dumped)
     assert np.max(np.abs(got - want) / np.abs(want)) < RTOL_R
@@ -158,8 +173,26 @@ def test_radix_pair_and_direct_paths_agree(fast, name):
     np.testing.assert_array_equal(res[fast._lib.ALGO_AUTO], res[fast._lib.ALGO_RADIX])
 
 
-@pytest.mark.parametrize('N,lo,P', [(164, 41, 82), (100, 35, 30), (20, 0, 20), (6, 1, 4), (300, 60, 180),
-                                    (1000, 400, 200), (1500, 500, 549), (256, 87, 82)])
+# (N, lo, P): every transform length M = 64 .. 2048 and every cell-pair class C = 5 .. 8 of the chirp-z kernels
+# (fast_b200/csrc/bluestein.cuh): M, C =
+CHIRP_Z_CASES = [(164, 41, 82),      # 256, 6  (the reference's auto-sized example grid)
+                 (100, 35, 30),      # 256, 5
+                 (200, 78, 44),      # 256, 7
+                 (236, 108, 20),     # 256, 8
+                 (20, 0, 20),        # 64, 5
+                 (6, 1, 4),          # 64, 5
+                 (58, 26, 6),        # 64, 8
+                 (104, 40, 24),      # 128, 7
+                 (120, 50, 8),       # 128, 8
+                 (300, 60, 180),     # 512, 5
+                 (460, 210, 50),     # 512, 8
+                 (700, 250, 200),    # 1024, 6
+                 (900, 400, 120),    # 1024, 8
+                 (1000, 400, 200),   # 2048, 5
+                 (1500, 500, 549)]   # 2048, 6
+
+
+@pytest.mark.parametrize('N,lo,P', CHIRP_Z_CASES)
 @pytest.mark.parametrize('fast_rng', [False, True])
 def test_chirp_z_path_matches_direct_dft(fast, N, lo, P, fast_rng):
     """Any even N: the Bluestein kernel (what AUTO runs when N is not a power of two) against the
@@ -184,6 +217,38 @@ def test_chirp_z_path_matches_direct_dft(fast, N, lo, P, fast_rng):
     np.testing.assert_allclose(outs[lib.ALGO_BLUESTEIN], outs[lib.ALGO_DIRECT], rtol=3e-4)
     if N & (N - 1):
         np.testing.assert_array_equal(outs[lib.ALGO_AUTO], outs[lib.ALGO_BLUESTEIN])
+
+
+@pytest.mark.parametrize('N,lo,P', [c for c in CHIRP_Z_CASES if c[0] <= 460])
+def test_chirp_z_path_with_host_noise_every_class(fast, N, lo, P):
+    """Caller-supplied noise (the reference-replay mode) through every chirp-z class against the direct DFT;
+    a power-of-two radix size is refused by the chirp-z path (its noise stride belongs to the radix kernel)."""
+    lib = fast._lib
+    dev = torch.device('cuda')
+    gen = torch.Generator(device='cuda').manual_seed(7 * N + P)
+    weight = lib.make_weight(torch.rand(N, N, dtype=torch.float64, device=dev, generator=gen) * 1e-5, 1.5)
+    U = torch.rand(P, P, dtype=torch.float32, device=dev, generator=gen)
+    noise = torch.randn(5, N, N, 2, dtype=torch.float32, device=dev, generator=gen)
+    chi = torch.zeros(10, dtype=torch.float32, device=dev)
+    outs = {}
+    for algo in (lib.ALGO_BLUESTEIN, lib.ALGO_DIRECT):
+        rp = lib.RunParams()
+        rp.n, rp.n_pup, rp.lo, rp.n_pairs, rp.pairs_per_chunk, rp.seed, rp.algo = N, P, lo, 5, 5, 1, algo
+        rp.u_sum, rp.sigma_chi = float(U.sum()), 0.0
+        ws = torch.empty(lib.screen_detect_workspace_bytes(rp), dtype=torch.uint8, device=dev)
+        a = torch.empty(5, dtype=torch.float32, device=dev)
+        b = torch.empty(5, dtype=torch.float32, device=dev)
+        lib.screen_detect(rp, weight, U, a, b, ws, chi=chi, noise=noise)
+        outs[algo] = torch.cat([a, b]).cpu().numpy()
+    np.testing.assert_allclose(outs[lib.ALGO_BLUESTEIN], outs[lib.ALGO_DIRECT], rtol=1e-4)
+
+
+def test_chirp_z_path_refuses_radix_sizes(fast):
+    lib = fast._lib
+    rp = lib.RunParams()
+    rp.n, rp.n_pup, rp.lo, rp.n_pairs, rp.pairs_per_chunk, rp.algo, rp.u_sum = 256, 82, 87, 1, 1, lib.ALGO_BLUESTEIN, 1.0
+    with pytest.raises(lib.FastbError, match='chirp-z'):
+        lib.screen_detect_workspace_bytes(rp)
 
 
 def test_chirp_z_path_with_reference_noise(fast):
@@ -587,7 +652,8 @@ def test_screens_match_reference_phs(fast, name):
     # and with device RNG against the oracle fed the restated Philox noise
     init = fo.build(p)
     scr = sim.screens(5, 1).cpu().numpy()
-    want = fo.screens_from_noise(fo.device_noise_pair(sim._run_seed(), 5, init['N'])[None],
+    want = fo.screens_from_noise(fo.device_noise_pair(sim._run_seed(), 5, init['N'],
+                                                      S=fo.noise_stride(init['N'], init['Npup']))[None],
                                  init['powerspec'], init['df'], init['lo'], init['hi'])
     if name != 'mini_subharm':
         assert rel(scr, want) < 2e-5
