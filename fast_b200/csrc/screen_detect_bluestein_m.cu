@@ -144,6 +144,7 @@ __global__ void __launch_bounds__(kBlueThreads, kBlueThreads <= 128 ? 4 : 2)
     constexpr bool kIdent = identity_layout();
     constexpr unsigned kKeep = C == 5 ? 0xffffu : keep_mask_low((18 - 2 * C) * S1);
     constexpr int kLinesPerWarp = S1 <= 32 ? 32 / S1 : 1;
+    constexpr bool kShuffle = F::kShflC && S1 == 32;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = a.n, P = a.n_pup;
@@ -262,7 +263,12 @@ __global__ void __launch_bounds__(kBlueThreads, kBlueThreads <= 128 ? 4 : 2)
                     sync();
                 }
             };
-            if (TWO) {
+            if constexpr (TWO && kShuffle) {
+                // M = 512: the last radix-2 stage on warp shuffles, as in the radix kernel of that size
+                F::template run_shfl<0xffffu>(u, v, twa, twb, buf, sync);
+                pointwise();
+                F::template run_shfl<kKeep>(u, v, twa, twb, buf, sync);
+            } else if (TWO) {
                 F::run(u, v, twa, twb, buf, sync);
                 pointwise();
                 F::run(u, v, twa, twb, buf, sync);

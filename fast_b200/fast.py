@@ -464,7 +464,10 @@ class Fast():
         self.shifts = self.shifts_sh = None
         U = numpy.ascontiguousarray(self.pupil * self.pupil_mode)
         self._u_sum = float(U.sum())
-        d['U'] = torch.from_numpy(U.astype(numpy.float32)).to(dev)
+        u32 = U.astype(numpy.float32)
+        self._u_digest = hash(u32.tobytes())       # sweep.run_sweep groups the samples that share U
+        d['U'] = torch.from_numpy(u32).to(dev)
+        self._u_version = d['U']._version
         if self.temporal:
             # per-step wind shifts in pixels (fast/fast.py:543-544) and the temporal log-amp PSD
             dts = numpy.arange(1, self.Niter_per_chunk + 1) * self.dt
@@ -689,19 +692,40 @@ class Fast():
             self._d['layer_screens'] = _lib.layer_screens(self._d['weight_per_layer'], self._run_seed(), noise=noise)
             self.interp_coords = self.pup_coords[numpy.newaxis, :, numpy.newaxis, :].astype(float) \
                 + self.pixel_shifts[:, :, :, numpy.newaxis]
-        coords = temporal.sample_coordinates(self.interp_coords, self.Npxls)
+        coords = self._advance_temporal_coords()
+        self._d['tcoords_host'] = coords
         self._d['tcoords'] = tuple(torch.from_numpy(c).to(self.device) for c in coords)
-        self.interp_coords = self.interp_coords + self.pixel_shifts[:, :, -1, numpy.newaxis, numpy.newaxis]
         return None
 
-    def _temporal_detector(self, chunk):
-        J = self.Niter_per_chunk
+    def _run_temporal(self):
+        """Every chunk of a TEMPORAL run in ONE detector launch: the per-chunk sample coordinates (the same host
+        arithmetic, chunk after chunk, as compute_phs_temporal: fast/fast.py:617-635) are stacked along the step
+        axis and staged once, instead of Nchunks rounds of bookkeeping + copies + launches (the run is
+        latency-bound at the reference's sizes).  Leaves the object in the state the chunk loop would."""
+        self.compute_phs_temporal(chunk=0)                  # layer screens + the coordinates of chunk 0
+        per_chunk = [self._d['tcoords_host']]
+        for i in range(1, self.Nchunks):
+            per_chunk.append(self._advance_temporal_coords())
+        xi, xf, yi, yf = (torch.from_numpy(numpy.concatenate([c[k] for c in per_chunk], axis=1)).to(self.device)
+                          for k in range(4))
+        self._d['tcoords'] = tuple(torch.from_numpy(c).to(self.device) for c in per_chunk[-1])
+        return self._temporal_detector(0, steps=self.Niter, coords=(xi, xf, yi, yf))
+
+    def _advance_temporal_coords(self):
+        """Sample coordinates of the next chunk from self.interp_coords, which is then moved on by the
+        chunk's total wind shift (fast/fast.py:621-635)."""
+        coords = temporal.sample_coordinates(self.interp_coords, self.Npxls)
+        self.interp_coords = self.interp_coords + self.pixel_shifts[:, :, -1, numpy.newaxis, numpy.newaxis]
+        return coords
+
+    def _temporal_detector(self, chunk, steps=None, coords=None):
+        J = self.Niter_per_chunk if steps is None else steps
         tp = _lib.TemporalParams()
         tp.n, tp.n_pup, tp.n_layers = self.Npxls, self.Npxls_pup, len(self.h)
         tp.coherent = 1 if self.params['COHERENT'] else 0
         tp.n_steps, tp.u_sum = J, self._u_sum
         out = torch.empty(J * (2 if tp.coherent else 1), dtype=torch.float32, device=self.device)
-        xi, xf, yi, yf = self._d['tcoords']
+        xi, xf, yi, yf = self._d['tcoords'] if coords is None else coords
         chi = self._d['chi'][chunk * J:(chunk + 1) * J].contiguous()
         _lib.temporal_detect(tp, self._d['layer_screens'], xi, xf, yi, yf, self._d['U'], chi, out)
         return torch.view_as_complex(out.view(-1, 2)) if tp.coherent else out
@@ -732,11 +756,7 @@ class Fast():
         ppc = self.Niter_per_chunk // 2
         total = self.Nchunks * ppc
         if self.temporal:
-            parts = []
-            for i in range(self.Nchunks):
-                self.compute_phs_temporal(chunk=i)
-                parts.append(self.compute_detector(chunk=i))
-            flat = torch.cat(parts)
+            flat = self._run_temporal()
         elif self.rng_mode != 'numpy':
             rank, world = dist.rank_world()
             lo, hi = dist.shard_range(total, rank, world)

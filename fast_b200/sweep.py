@@ -28,8 +28,10 @@ def _group_key(sim):
     if sim.temporal or sim.rng_mode == 'numpy' or sim.subharmonics:
         return None
     U = sim._d['U']
+    # the digest taken at construction stands while the device copy has not been written to since
+    digest = sim._u_digest if U._version == sim._u_version else hash(U.cpu().numpy().tobytes())
     return (str(sim.device), sim.Npxls, sim.Npxls_pup, sim._lo, sim.Niter, sim.Nchunks,
-            bool(sim.params['COHERENT']), sim.rng_mode, sim._u_sum, hash(U.cpu().numpy().tobytes()))
+            bool(sim.params['COHERENT']), sim.rng_mode, sim._u_sum, digest)
 
 
 def run_batch(sims, stats=None):
