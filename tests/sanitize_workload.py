@@ -48,6 +48,22 @@ ws = torch.empty(_lib.screen_detect_workspace_bytes(rp), dtype=torch.uint8, devi
 oa = torch.empty(2, dtype=torch.float32, device='cuda'); ob = torch.empty_like(oa)
 _lib.screen_detect(rp, wt, torch.ones(P, P, dtype=torch.float32, device='cuda'), oa, ob, ws)
 assert torch.isfinite(oa).all()
+# the chirp-z kernels over transform lengths and cell classes (M = 64 .. 1024; M = 512 runs the shuffle last stage),
+# device RNG and caller-supplied noise
+for N, lo, P in ((58, 26, 6), (104, 40, 24), (236, 108, 20), (200, 78, 44), (300, 60, 180), (460, 210, 50), (700, 250, 200)):
+    rp = _lib.RunParams()
+    rp.n, rp.n_pup, rp.lo, rp.n_pairs, rp.pairs_per_chunk, rp.seed, rp.algo = N, P, lo, 3, 3, 17, _lib.ALGO_AUTO
+    rp.u_sum, rp.sigma_chi = float(P * P), 0.02
+    wt = _lib.make_weight(torch.rand(N, N, dtype=torch.float64, device='cuda') * 1e-6, 1.0)
+    ws = torch.empty(_lib.screen_detect_workspace_bytes(rp), dtype=torch.uint8, device='cuda')
+    oa = torch.empty(3, dtype=torch.float32, device='cuda'); ob = torch.empty_like(oa)
+    U1 = torch.ones(P, P, dtype=torch.float32, device='cuda')
+    _lib.screen_detect(rp, wt, U1, oa, ob, ws)
+    assert torch.isfinite(oa).all()
+    if N <= 300:
+        nz = torch.randn(3, N, N, 2, dtype=torch.float32, device='cuda')
+        _lib.screen_detect(rp, wt, U1, oa, ob, ws, chi=torch.zeros(6, dtype=torch.float32, device='cuda'), noise=nz)
+        assert torch.isfinite(ob).all()
 x = np.exp(0.3 * np.random.default_rng(0).standard_normal(5000)).astype(np.float32)
 comms.ber_ook(np.array([3.0, 9.0]), x); comms.sep_qam(16, 10.0, x)
 comms.fade_prob(x, np.array([0.5, 0.9])); comms.fade_dur(x, 0.8)
