@@ -27,6 +27,30 @@ struct BlueGeom {
     int log2m, M, S1, C;
 };
 BlueGeom blue_geom(int n, int n_pup);
+// class of an N-point grid on S1 threads per line: cell pairs per thread, at least 5
+FASTB_HD constexpr int blue_cell_pairs(int n, int s1) {
+    const int mc = (n + s1 - 1) / s1, c = (mc + 1) / 2;
+    return c < 5 ? 5 : c;
+}
+// outputs a problem of class C can want: below (18 - 2C) S1 (any for the catch-all class 5)
+FASTB_HD constexpr int blue_output_bound(int c, int s1) { return c == 5 ? 16 * s1 : (18 - 2 * c) * s1; }
+// does the transform F leave output k = u + S1 e in register e of thread u, i.e. in its own input order?
+template <class F>
+constexpr bool blue_identity_layout() {
+    for (int u = 0; u < F::S1; ++u)
+        for (int e = 0; e < 16; ++e)
+            if (F::k_out(u, e) != u + F::S1 * e) return false;
+    return true;
+}
+// registers of F that can hold an output below `w`
+template <class F>
+constexpr unsigned blue_keep_mask_low(int w) {
+    unsigned m = 0;
+    for (int u = 0; u < F::S1; ++u)
+        for (int e = 0; e < 16; ++e)
+            if (F::k_out(u, e) < w) m |= 1u << e;
+    return m;
+}
 // complex chirped weight copies, one float4 per cell pair: entry (row r, pair j < C, thread u) at
 // (r C + j) S1 + u holds wc[r][u + S1 2j], wc[r][u + S1 (2j + 1)], wc = weight c[col] c[row] (0 beyond N)
 size_t bluestein_weight_bytes(int n, int n_pup, int n_items);

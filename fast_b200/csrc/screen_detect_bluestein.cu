@@ -79,8 +79,7 @@ BlueGeom blue_geom(int n, int n_pup) {
     g.log2m = blue_log2m(n, n_pup);
     g.M = 1 << g.log2m;
     g.S1 = g.M / 16;
-    const int mc = (n + g.S1 - 1) / g.S1;            // cells per thread that can lie inside the grid
-    g.C = (mc + 1) / 2 < 5 ? 5 : (mc + 1) / 2;
+    g.C = blue_cell_pairs(n, g.S1);
     return g;
 }
 

@@ -36,22 +36,6 @@ constexpr int kM = F::N, kS1 = F::S1;
 constexpr int kBlueThreads = kLog2M <= 8 ? 128 : 256;
 constexpr int kRowB = 18;                     // float2 per Bhat row (16 used): 144-byte rows, conflict-free 128-bit loads
 
-// does the transform leave output k = u + S1 e in register e of thread u, i.e. in its own input order?
-constexpr bool identity_layout() {
-    for (int u = 0; u < F::S1; ++u)
-        for (int e = 0; e < 16; ++e)
-            if (F::k_out(u, e) != u + F::S1 * e) return false;
-    return true;
-}
-// registers that can hold an output below `w`
-constexpr unsigned keep_mask_low(int w) {
-    unsigned m = 0;
-    for (int u = 0; u < F::S1; ++u)
-        for (int e = 0; e < 16; ++e)
-            if (F::k_out(u, e) < w) m |= 1u << e;
-    return m;
-}
-
 // ---- tables -------------------------------------------------------------------------------------------
 // block b < 16 S1: Bhat entry (u, e) = (b / 16, b % 16); the blocks after that write the output chirp
 __global__ void __launch_bounds__(256) blue_tables_kernel(int N, int lo, int P, float2* __restrict__ bhatp,
@@ -141,8 +125,8 @@ __global__ void __launch_bounds__(kBlueThreads, kBlueThreads <= 128 ? 4 : 2)
     constexpr int NC = 2 * C;                                   // cells per thread
     static_assert(THREADS % S1 == 0 && LPB >= 1 && (S1 <= 32 || LPB <= 15), "line/barrier layout");
     static_assert(C >= 5 && C <= 8, "cell-pair class");
-    constexpr bool kIdent = identity_layout();
-    constexpr unsigned kKeep = C == 5 ? 0xffffu : keep_mask_low((18 - 2 * C) * S1);
+    constexpr bool kIdent = blue_identity_layout<F>();
+    constexpr unsigned kKeep = blue_keep_mask_low<F>(blue_output_bound(C, S1));
     constexpr int kLinesPerWarp = S1 <= 32 ? 32 / S1 : 1;
     constexpr bool kShuffle = F::kShflC && S1 == 32;
 

@@ -71,8 +71,8 @@ def run_batch(sims, stats=None):
             out_b = torch.view_as_complex(out_b.view(-1, 2))
         a, b = dist.gather_pairs(out_a, out_b, E * ppi, world)
         # per sample: the reference's order (chunk-major, Re half then Im half), then one D2H copy
-        flat = torch.stack([dist.assemble(a[e * ppi:(e + 1) * ppi], b[e * ppi:(e + 1) * ppi], lead.Nchunks, ppc)
-                            for e in range(E)])
+        # (dist.assemble for every item at once: [item][chunk][Re half | Im half][pair])
+        flat = torch.stack([a.reshape(E, lead.Nchunks, ppc), b.reshape(E, lead.Nchunks, ppc)], dim=2).reshape(E, -1)
         wide = flat.to(torch.complex128 if flat.is_complex() else torch.float64)
         dls = torch.tensor([sim.diffraction_limit for sim in sims], dtype=torch.float64, device=dev)
         host = lead._to_host(wide.reshape(-1)).reshape(E, -1)
