@@ -23,6 +23,8 @@ COMMON = ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC', '--expt-relax
 _DBG = ['-DFASTB_TUNE_DBG'] if os.environ.get('FASTB_TUNE_DBG') else []
 if os.environ.get('FASTB_SPLIT'):              # tuning builds: FASTB_SPLIT=0 -> LineFFT for N >= 512
     _DBG += ['-DFASTB_SPLIT=' + os.environ['FASTB_SPLIT']]
+if os.environ.get('FASTB_PF'):                 # tuning builds: pass-2 column prefetch through L1 (screen_detect_kernel.cuh)
+    _DBG += ['-DFASTB_PF=' + os.environ['FASTB_PF']]
 if os.environ.get('FASTB_SCALAR_STAGES'):      # tuning builds: which FFT stages use scalar FP32 (fft_core.cuh)
     _DBG += ['-DFASTB_SCALAR_STAGES=' + os.environ['FASTB_SCALAR_STAGES']]
 # object name -> (source, extra flags).  The radix kernels of K2 are compiled once per grid size
@@ -63,6 +65,7 @@ def _digest():
     h.update(os.environ.get('FASTB_SCALAR_STAGES', '').encode())
     h.update(os.environ.get('FASTB_SPLIT', '').encode())
     h.update(os.environ.get('FASTB_BLUE_TWO', '').encode())
+    h.update(os.environ.get('FASTB_PF', '').encode())
     return h.hexdigest()
 
 

@@ -425,6 +425,12 @@ struct RadixCfg<LOG2N, 32> {
 // output, and the compiler drops the last-stage butterflies (and shared loads) that feed the others.
 // SHFL: the last radix-2 / radix-4 stage of N = 512 / 1024 runs on warp shuffles (fft_core.cuh,
 // phase_c_shfl) instead of a second shared-memory exchange.
+// FASTB_PF=1 (tuning builds): pass 2 reads its columns through L1 and touches the next column one iteration ahead.
+// Measured without effect (C2 -0.05 %, C4 -1.4 %, C5 +0.2 %; profiles/experiments_r02.txt, 15): the long-scoreboard
+// samples of pass 2 (8 % of all at C2) are latency the other warps already cover.
+#ifndef FASTB_PF
+#define FASTB_PF 0
+#endif
 template <int N>
 constexpr int window_half(int win) { return win == 1 ? N / 8 : win == 2 ? 3 * N / 16 : win == 3 ? N / 4 : N; }
 
@@ -443,6 +449,7 @@ __global__ void __launch_bounds__(THREADS, MINB) screen_detect_radix(const __gri
     constexpr bool kTmaW = kTma && (TMA == 1 || TMA == 3);      // weight rows through the stage
     constexpr bool kTmaT = kTma && (TMA == 1 || TMA == 2);      // scratch columns through the stage
     constexpr bool kShfl = SHFL && F::kShflC;
+    constexpr bool kPrefetch = FASTB_PF != 0 && !kTma && !ONCHIP;
     constexpr int kLinesPerWarp = S1 <= 32 ? 32 / S1 : 1;
     constexpr int kWarps = THREADS / 32;
     constexpr int kStageBytes = 32 * E * 8;
@@ -632,6 +639,19 @@ __global__ void __launch_bounds__(THREADS, MINB) screen_detect_radix(const __gri
                 const float2* tcol = Ts + (size_t)(line < P ? line : 0) * NP;
 #pragma unroll
                 for (int m = 0; m < E; ++m) v[m] = tcol[u + S1 * m];
+            } else if (kPrefetch) {
+                // the column through L1, and one word of each 128-byte line of the NEXT column touched now, so that
+                // its loads hit L1 an iteration later instead of waiting for L2 (pass 2 spent 18 % of its FFT
+                // samples and 35 % of its detector samples on the long scoreboard).  T is only read after the
+                // barrier that follows its last store, and the SM's own stores keep its L1 coherent.
+                const float2* tcol = T + (size_t)(line < P ? line : 0) * N;
+#pragma unroll
+                for (int m = 0; m < E; ++m) v[m] = __ldca(tcol + u + S1 * m);
+                const int nxt = line + LPB < P ? line + LPB : P - 1;
+                unsigned touch;
+                asm volatile("ld.global.ca.b32 %0, [%1];" : "=r"(touch) : "l"(T + (size_t)nxt * N + (E * u)));
+                if (u < (P * 4 + 127) / 128)
+                    asm volatile("ld.global.ca.b32 %0, [%1];" : "=r"(touch) : "l"(a.u_t + (size_t)nxt * P + min(32 * u, P - 1)));
             } else {
                 const float2* tcol = T + (size_t)(line < P ? line : 0) * N;
 #pragma unroll
