@@ -652,7 +652,9 @@ def run_ours(args):
     u_host = sim._d['U'].cpu().pin_memory()
     width = 2 if coherent else 1
     h2d = w_host.numel() * 4 + u_host.numel() * 4
-    d2h = world * n_real * width * 4           # Fast.run() leaves the WHOLE result array on every rank
+    # Fast.run() leaves the WHOLE result on every rank: two float64 arrays (result._r and I = result.power,
+    # widened on the device) cross to pinned host memory per step
+    d2h = world * n_real * width * 8 * 2
 
     def e2e_step():
         sim._d['weight'].copy_(w_host, non_blocking=True)
@@ -660,7 +662,8 @@ def run_ours(args):
         sim.run()                              # fast/fast.py:115-140 contract: FastResult on the host,
         return sim.I                           # sim.I = result.power (fast/fast.py:137), float64
 
-    power = e2e_step()
+    for _ in range(3):                         # untimed: the pinned result blocks of the host allocator exist afterwards
+        power = e2e_step()
     if world > 1:
         td.barrier()
     torch.cuda.synchronize()

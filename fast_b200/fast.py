@@ -29,6 +29,10 @@ from . import temporal
 
 logger = logging.getLogger(__name__)
 
+# the reference's optional-dependency flag (fast/fast.py:9-15, read by test/tests_pytest.py:50): pyFFTW is never
+# used on this path
+_pyfftw = False
+
 _AO_MODES = {'NOAO': _lib.AO_NOAO, 'AO': _lib.AO_AO, 'TT': _lib.AO_AO, 'LGSAO': _lib.AO_LGSAO}
 _RNG_MODES = ('device', 'device-fast', 'numpy')
 _GOLDEN64 = 0x9E3779B97F4A7C15
@@ -96,6 +100,11 @@ class SpatialFrequencyStruct():
     def fabs(self):
         return numpy.sqrt(self.fx ** 2 + self.fy ** 2)
 
+    def realspace_sampling(self):
+        """Pixel scales of the real-space grid conjugate to this one (fast/fast.py:923-928)."""
+        Nx, Ny = self.fx.shape[-1], self.fx.shape[-2]
+        return 2 * numpy.pi / (Nx * self.dfx), 2 * numpy.pi / (Ny * self.dfy)
+
 
 class SpatialFrequencies():
     """fast/fast.py:814-875: `main` grid with df = 2 pi / (N dx); `temporal` per-layer grids."""
@@ -109,6 +118,18 @@ class SpatialFrequencies():
     fx = property(lambda self: self.main.fx)
     fy = property(lambda self: self.main.fy)
     fabs = property(lambda self: self.main.fabs)
+
+    def make_main_freqs(self, N, dx):
+        """fast/fast.py:830-833 (the constructor already calls it)."""
+        self.main = SpatialFrequencyStruct(numpy.arange(-N / 2., N / 2.) * (2 * numpy.pi / (N * dx)))
+
+    def make_logamp_freqs(self, Nx=None, dx=None, Ny=None, dy=None):
+        """Grid of the log-amplitude PSD: the main grid unless a sampling is given (fast/fast.py:866-875)."""
+        if Nx is None and dx is None:
+            self.logamp = self.main
+        else:
+            self.logamp = SpatialFrequencyStruct(numpy.arange(-Nx / 2., Nx / 2.) * (2 * numpy.pi / (Nx * dx)),
+                                                 numpy.arange(-Ny / 2., Ny / 2.) * (2 * numpy.pi / (Ny * dy)))
 
     def make_subharm_freqs(self, pmax=3):
         """Three 3 x 3 levels spaced 2 pi / (3^p N dx) (fast/fast.py:835-844)."""
@@ -367,6 +388,11 @@ class Fast():
             ft = self.freq.temporal
             self.pupil_filter_temporal = temporal.elongated_pupil_filter(self, ft.fx_axis, ft.fy_axis)
         return self.pupil
+
+    def init_fftw(self):
+        """fast/fast.py:419-438 plans pyFFTW transforms; the transforms of this path are the K2 / K4 kernels, so
+        there is nothing to plan (FFTW / FFTW_THREADS are accepted and ignored)."""
+        self.fftw_objs = {}
 
     def init_phs_logamp(self):
         # screens are never materialised on this path; `logamp` holds the host draws in

@@ -116,3 +116,20 @@ def test_temporal_host_bookkeeping_matches_oracle(name):
         np.testing.assert_allclose(yi + yf.astype(float), atc[:, 1], atol=2e-5)
         assert xi.min() >= 0 and xi.max() <= N - 2 and 0 <= xf.min() and xf.max() <= 1
         interp = interp + shifts[:, :, -1, None, None]
+
+
+def test_spatial_frequency_helpers_follow_the_reference():
+    """fast/fast.py:830-833, 866-875, 923-928: main / log-amplitude grids and the conjugate real-space sampling."""
+    from fast_b200 import fast as fb
+    fr = fb.SpatialFrequencies(64, 0.04)
+    assert fr.main.df == pytest.approx(2 * np.pi / (64 * 0.04))
+    dx, dy = fr.main.realspace_sampling()
+    assert dx == pytest.approx(0.04) and dy == pytest.approx(0.04)
+    fr.make_logamp_freqs()
+    assert fr.logamp is fr.main
+    fr.make_logamp_freqs(Nx=32, dx=0.02, Ny=16, dy=0.05)
+    assert fr.logamp.fx.shape == (16, 32)
+    assert fr.logamp.dfx == pytest.approx(2 * np.pi / (32 * 0.02)) and fr.logamp.dfy == pytest.approx(2 * np.pi / (16 * 0.05))
+    assert fr.logamp.realspace_sampling() == pytest.approx((0.02, 0.05))
+    fr.make_main_freqs(128, 0.01)
+    assert fr.main.fx_axis.shape == (128,) and fr.main.fx_axis[64] == 0.0
