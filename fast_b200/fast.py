@@ -729,13 +729,20 @@ class Fast():
         axis and staged once, instead of Nchunks rounds of bookkeeping + copies + launches (the run is
         latency-bound at the reference's sizes).  Leaves the object in the state the chunk loop would."""
         self.compute_phs_temporal(chunk=0)                  # layer screens + the coordinates of chunk 0
-        per_chunk = [self._d['tcoords_host']]
-        for i in range(1, self.Nchunks):
-            per_chunk.append(self._advance_temporal_coords())
-        xi, xf, yi, yf = (torch.from_numpy(numpy.concatenate([c[k] for c in per_chunk], axis=1)).to(self.device)
-                          for k in range(4))
-        self._d['tcoords'] = tuple(torch.from_numpy(c).to(self.device) for c in per_chunk[-1])
-        return self._temporal_detector(0, steps=self.Niter, coords=(xi, xf, yi, yf))
+        # interp_coords chunk after chunk (the same accumulation as the chunk loop), then ONE pass of the coordinate
+        # bookkeeping over the stacked array: the numpy calls are overhead-bound at (L, 2, J, Npup)
+        step = self.pixel_shifts[:, :, -1, numpy.newaxis, numpy.newaxis]
+        first = self.interp_coords - step                   # what chunk 0 sampled (compute_phs_temporal moved on)
+        stack = [first]
+        for _ in range(1, self.Nchunks):
+            stack.append(stack[-1] + step)
+        self.interp_coords = stack[-1] + step
+        coords = temporal.sample_coordinates(numpy.stack(stack), self.Npxls)       # each (Nchunks, L, J, Npup)
+        L = coords[0].shape[1]
+        staged = tuple(torch.from_numpy(numpy.ascontiguousarray(c.transpose(1, 0, 2, 3)).reshape(L, self.Niter, -1))
+                       .to(self.device) for c in coords)
+        self._d['tcoords'] = tuple(torch.from_numpy(numpy.ascontiguousarray(c[-1])).to(self.device) for c in coords)
+        return self._temporal_detector(0, steps=self.Niter, coords=staged)
 
     def _advance_temporal_coords(self):
         """Sample coordinates of the next chunk from self.interp_coords, which is then moved on by the

@@ -57,19 +57,31 @@ def temporal_logamp_powerspec(sim, fx_axes, fy_axes, fabs, spline):
 
 
 def sample_coordinates(interp_coords, N):
-    """(L, 2, J, Npup) wind-shifted pupil coordinates -> integer/fraction sample positions
+    """(..., L, 2, J, Npup) wind-shifted pupil coordinates -> integer/fraction sample positions
     per output pixel, reproducing fast/fast.py:621-633 literally: wrap mod N, sort, roll back
     by the argmax of the gaps (0 without wrap; one short of the true inverse with a wrap, which
-    is what the reference computes), then FITPACK's clamp of arguments beyond the last knot."""
-    coord = numpy.sort(interp_coords % N, axis=-1)
+    is what the reference computes), then FITPACK's clamp of arguments beyond the last knot.
+    Same values as the plain numpy statement (tests/test_host_mirror.py keeps it), with the two
+    slow steps -- the float modulo and the per-row roll -- applied only where they do something."""
+    x = numpy.asarray(interp_coords, dtype=float)
+    outside = (x < 0) | (x >= N)
+    wrapped = x.copy()
+    if outside.any():
+        wrapped[outside] = x[outside] % N          # x % N == x for 0 <= x < N
+    coord = numpy.sort(wrapped, axis=-1)
     gaps = numpy.abs(numpy.diff(coord, axis=-1))
     roll = gaps.argmax(-1)
-    roll[numpy.isclose(gaps, 1).all(-1)] = 0
+    roll[(numpy.abs(gaps - 1) <= 1e-8 + 1e-5).all(-1)] = 0        # numpy.isclose(gaps, 1), spelled out
     npup = coord.shape[-1]
-    at = numpy.take_along_axis(coord, (numpy.arange(npup) + roll[..., None]) % npup, axis=-1)
+    at = coord
+    rows = numpy.nonzero(roll)
+    if rows[0].size:
+        at = coord.copy()
+        sel = coord[rows]                                          # (n_rolled, Npup)
+        at[rows] = numpy.take_along_axis(sel, (numpy.arange(npup) + roll[rows][:, None]) % npup, axis=-1)
     at = numpy.minimum(at, N - 1.0)
     i0 = numpy.minimum(numpy.floor(at).astype(numpy.int32), N - 2)
     frac = (at - i0).astype(numpy.float32)
-    # -> xi, xf, yi, yf each (L, J, Npup)
-    return (numpy.ascontiguousarray(i0[:, 0]), numpy.ascontiguousarray(frac[:, 0]),
-            numpy.ascontiguousarray(i0[:, 1]), numpy.ascontiguousarray(frac[:, 1]))
+    # -> xi, xf, yi, yf each (L, J, Npup); leading axes (e.g. one per chunk) are kept
+    return (numpy.ascontiguousarray(i0[..., 0, :, :]), numpy.ascontiguousarray(frac[..., 0, :, :]),
+            numpy.ascontiguousarray(i0[..., 1, :, :]), numpy.ascontiguousarray(frac[..., 1, :, :]))

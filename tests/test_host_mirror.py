@@ -133,3 +133,36 @@ def test_spatial_frequency_helpers_follow_the_reference():
     assert fr.logamp.realspace_sampling() == pytest.approx((0.02, 0.05))
     fr.make_main_freqs(128, 0.01)
     assert fr.main.fx_axis.shape == (128,) and fr.main.fx_axis[64] == 0.0
+
+
+def _sample_coordinates_plain(interp_coords, N):
+    """The literal numpy statement of fast/fast.py:621-633 that temporal.sample_coordinates must reproduce."""
+    coord = np.sort(interp_coords % N, axis=-1)
+    gaps = np.abs(np.diff(coord, axis=-1))
+    roll = gaps.argmax(-1)
+    roll[np.isclose(gaps, 1).all(-1)] = 0
+    npup = coord.shape[-1]
+    at = np.take_along_axis(coord, (np.arange(npup) + roll[..., None]) % npup, axis=-1)
+    at = np.minimum(at, N - 1.0)
+    i0 = np.minimum(np.floor(at).astype(np.int32), N - 2)
+    frac = (at - i0).astype(np.float32)
+    return i0[..., 0, :, :], frac[..., 0, :, :], i0[..., 1, :, :], frac[..., 1, :, :]
+
+
+@pytest.mark.parametrize('scale', [0.0, 3.0, 40.0, 400.0])
+def test_temporal_sample_coordinates_equal_the_plain_statement(scale):
+    """No wrap, partial wraps (negative and beyond N), many wraps; with and without a leading chunk axis."""
+    from fast_b200 import temporal
+    rng = np.random.default_rng(int(scale) + 1)
+    L, J, P, N = 3, 7, 22, 64
+    pup = np.stack([np.arange(P) + 21.0, np.arange(P) + 21.0])
+    shifts = (rng.random((L, 2, J)) - 0.5) * scale
+    ic = pup[None, :, None, :] + shifts[:, :, :, None]
+    ic[0, 0, 0] = np.arange(P) + 42.0            # reaches exactly N - 1 + ... and the last knot
+    stacked = np.stack([ic, ic + shifts[:, :, -1, None, None], ic - 17.25])
+    for arr in (ic, stacked):
+        got = temporal.sample_coordinates(arr, N)
+        want = _sample_coordinates_plain(arr, N)
+        for g, w in zip(got, want):
+            np.testing.assert_array_equal(g, w)
+            assert g.flags['C_CONTIGUOUS']
