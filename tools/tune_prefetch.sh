@@ -1,5 +1,6 @@
 #!/bin/bash
-# GPU session r03c: pass-2 column prefetch through L1 (FASTB_PF=1 tuning library) vs product, CTA shape 256x3 at C2
+# Experiment 15 (profiles/experiments_r02.txt): pass-2 column prefetch through L1 and more resident warps against the
+# product kernel.  Needs the tuning library:  FASTB_TUNE=1 FASTB_TUNE_TAG=_pf FASTB_PF=1 python build_fastb.py
 mkdir -p gpurun_out
 one() {  # label, workload, env...
   label=$1; w=$2; shift 2
