@@ -1,10 +1,10 @@
 """Reference distributions for the statistical parity checks (TEST INFRASTRUCTURE).
 
-    python oracle/make_golden_dist.py [c2|c3_el10|c4|c5]
+    python oracle/make_golden_dist.py [c2|c3_el10|c4|c5|c1prime]
 
 Runs the UNMODIFIED reference in 8 processes with distinct seeds and stores the per-realisation
 values `_r` in tests/golden/<case>_dist_*.npz (c2: 1e5 samples, float32; c3_el10: 5e4; c4: 5e4
-complex64; c5: 1e4).  The CUDA path with device RNG must reproduce these distributions (mean /
+complex64; c5: 1e4; c1prime -- the auto-sized 164 x 164 grid of the reference's example, TEMPORAL off: 1e5).  The CUDA path with device RNG must reproduce these distributions (mean /
 variance of dB_rel, KS test) -- tests/test_gpu_statistics.py.
 """
 import os
@@ -20,6 +20,7 @@ CASES = {
     'c3_el10': ('c3_elevation', {'el_deg': 10.0}, 6250, 25, 'c3_el10_dist_5e4.npz'),
     'c4': ('c4', {}, 6250, 125, 'c4_dist_5e4.npz'),
     'c5': ('c5', {}, 1250, 125, 'c5_dist_1e4.npz'),
+    'c1prime': ('c1prime', {}, 12500, 50, 'c1prime_dist_1e5.npz'),
 }
 
 

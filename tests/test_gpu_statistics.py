@@ -151,3 +151,16 @@ def test_c5_large_grid_distribution_matches_reference(rng):
     _, p = load_golden('c5')
     sim = fast_b200.Fast(dict(p, NITER=100000, NCHUNKS=10, SEED=9, RNG=rng))
     _compare_db(sim.run().dB_rel, 10 * np.log10(ref), 'c5')
+
+
+@pytest.mark.parametrize('rng', RNGS)
+def test_c1prime_auto_grid_distribution_matches_reference(rng):
+    """C1' (the reference's example config, TEMPORAL off: auto-sized 164 x 164 grid, uplink): the chirp-z kernel,
+    whose noise blocks follow the transform length (stride M / 16 = 16 instead of ceil(N / 16) = 11), against 1e5
+    realisations of the unmodified reference."""
+    import fast_b200
+    ref = _golden_dist('c1prime_dist_1e5.npz').astype(float)
+    _, p = load_golden('c1prime')
+    sim = fast_b200.Fast(dict(p, NITER=1000000, NCHUNKS=10, SEED=164, RNG=rng))
+    assert sim.Npxls == 164
+    _compare_db(sim.run().dB_rel, 10 * np.log10(ref), 'c1prime')
