@@ -189,7 +189,9 @@ CHIRP_Z_CASES = [(164, 41, 82),      # 256, 6  (the reference's auto-sized examp
                  (700, 250, 200),    # 1024, 6
                  (900, 400, 120),    # 1024, 8
                  (1000, 400, 200),   # 2048, 5
-                 (1500, 500, 549)]   # 2048, 6
+                 (1500, 500, 549),   # 2048, 6
+                 (164, 41, 81),      # odd crops
+                 (22, 1, 19)]
 
 
 @pytest.mark.parametrize('N,lo,P', CHIRP_Z_CASES)
@@ -657,3 +659,31 @@ def test_screens_match_reference_phs(fast, name):
                                  init['powerspec'], init['df'], init['lo'], init['hi'])
     if name != 'mini_subharm':
         assert rel(scr, want) < 2e-5
+
+
+def test_chirp_z_grid_in_every_run_mode(fast):
+    """The auto-sized 164 x 164 grid (chirp-z kernel) through the modes the radix tests cover on powers of two:
+    any split of the pair range gives the same values, |coherent z|^2 equals the incoherent result, a batched sweep
+    equals the per-sample runs bit for bit with per-sample statistics, successive runs are fresh."""
+    from fast_b200 import configs, sweep
+    p = configs.c1prime(niter=96, nchunks=4, seed=21)
+    sim = fast.Fast(dict(p))
+    assert sim.Npxls == 164 and fast._lib.noise_stride(164, sim.Npxls_pup) == 16
+    a, b = sim.screen_detect(0, 48)
+    a1, b1 = sim.screen_detect(0, 17)
+    a2, b2 = sim.screen_detect(17, 31)
+    assert torch.equal(a, torch.cat([a1, a2])) and torch.equal(b, torch.cat([b1, b2]))
+    r_inc = fast.Fast(dict(p)).run()._r
+    z = fast.Fast(dict(p, COHERENT=True)).run()._r
+    assert z.dtype == complex
+    np.testing.assert_allclose(np.abs(z) ** 2, r_inc, rtol=2e-6)
+    ps = [dict(p, SEED=300 + i, ZENITH_ANGLE=zen) for i, zen in enumerate((20.0, 45.0, 65.0))]
+    sims = sweep.build_sims(ps)
+    res = sweep.run_sweep(sims, stats=True, db_lo=-50, db_hi=5, nbins=110)
+    again = [r._r.copy() for r in sweep.run_sweep(sims)]
+    for q, r, r2, s_ in zip(ps, res, again, sims):
+        solo = fast.Fast(dict(q))
+        np.testing.assert_array_equal(r._r, solo.run()._r)
+        np.testing.assert_array_equal(r2, solo.run()._r)
+        assert not np.array_equal(r._r, r2)
+        assert s_.stats['n'] == 96 and s_.stats['mean'] == pytest.approx(r._r.mean(), rel=1e-6)
