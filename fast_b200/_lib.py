@@ -129,6 +129,7 @@ _SIGS = {
     'fastb_layer_screens': (C.c_int, [C.c_int32, C.c_int32, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_int64, C.c_void_p]),
     'fastb_temporal_detect': (C.c_int, [C.POINTER(TemporalParams)] + [C.c_void_p] * 8 + [C.c_void_p]),
+    'fastb_temporal_coords': (C.c_int, [C.c_int32] * 6 + [C.c_void_p] * 5 + [C.c_void_p]),
     'fastb_stats': (C.c_int, [C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_int32, C.c_void_p,
                               C.c_void_p, C.c_void_p, C.c_void_p]),
     'fastb_error_curve': (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
@@ -346,6 +347,22 @@ def layer_screens(weight_per_layer, seed, noise=None):
     _check(lib.fastb_layer_screens(n, L, int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(weight_per_layer, torch.float32),
                                    _ptr(nz), _ptr(out), _ptr(ws), nbytes, _stream()), 'fastb_layer_screens')
     return out
+
+
+def temporal_coords(n, n_pup, lo, pixel_shifts, n_chunks):
+    """K4c: (L, 2, J) float64 per-step pixel shifts -> xi, xf, yi, yf, each (L, n_chunks * J, n_pup), for every step
+    of a run (the reference's chunk-after-chunk coordinate bookkeeping, fast/fast.py:617-635)."""
+    L, _, J = pixel_shifts.shape
+    dev = pixel_shifts.device
+    shape = (L, int(n_chunks) * J, int(n_pup))
+    xi = torch.empty(shape, dtype=torch.int32, device=dev)
+    yi = torch.empty(shape, dtype=torch.int32, device=dev)
+    xf = torch.empty(shape, dtype=torch.float32, device=dev)
+    yf = torch.empty(shape, dtype=torch.float32, device=dev)
+    _check(lib.fastb_temporal_coords(int(n), int(n_pup), int(lo), L, J, int(n_chunks), _ptr(pixel_shifts, torch.float64),
+                                     _ptr(xi, torch.int32), _ptr(xf, torch.float32), _ptr(yi, torch.int32),
+                                     _ptr(yf, torch.float32), _stream()), 'fastb_temporal_coords')
+    return xi, xf, yi, yf
 
 
 def temporal_detect(tp: TemporalParams, screens, xi, xf, yi, yf, U, chi, out):

@@ -204,6 +204,130 @@ extern "C" int fastb_layer_screens(int32_t n, int32_t n_layers, uint64_t seed, c
     return check_launch("screens_cols_kernel");
 }
 
+namespace fastb {
+namespace {
+
+// ---- K4c: sample coordinates of every time step (fast/fast.py:617-635), one block per (layer, axis, step) row ----
+// The reference's bookkeeping, operation for operation in float64 so that the integer / fraction pairs are the ones
+// numpy produces: x_p = (lo + p) + shift[l][axis][j], moved on by the chunk's total shift once per earlier chunk;
+// wrap with numpy's float modulo; sort; roll back by the first argmax of the gaps (0 when every gap is 1 within
+// numpy.isclose); FITPACK's clamp at the last knot; floor / fraction.
+__global__ void __launch_bounds__(kThreads) temporal_coords_kernel(int n, int n_pup, int lo, int n_layers, int J,
+                                                                   int n_chunks, const double* __restrict__ shifts,
+                                                                   int* __restrict__ xi, float* __restrict__ xf,
+                                                                   int* __restrict__ yi, float* __restrict__ yf) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* c = reinterpret_cast<double*>(smem_raw);             // np2 sorted coordinates (+inf padded)
+    __shared__ double red_v[kThreads];
+    __shared__ int red_i[kThreads];
+    __shared__ int all_close, roll_s;
+    const int tid = threadIdx.x, P = n_pup;
+    int np2 = 1;
+    while (np2 < P) np2 <<= 1;
+    const long long n_steps = (long long)J * n_chunks;
+    const long long row = blockIdx.x;                            // ((l * 2 + axis) * n_steps + step)
+    const long long step = row % n_steps;
+    const int axis = (int)((row / n_steps) % 2), l = (int)(row / (2 * n_steps));
+    const int chunk = (int)(step / J), j = (int)(step % J);
+    const double sh = shifts[((size_t)l * 2 + axis) * J + j], last = shifts[((size_t)l * 2 + axis) * J + (J - 1)];
+    const double dn = (double)n;
+    for (int p = tid; p < np2; p += kThreads) {
+        double x = INFINITY;
+        if (p < P) {
+            x = __dadd_rn((double)(lo + p), sh);
+            for (int k = 0; k < chunk; ++k) x = __dadd_rn(x, last);
+            double r = fmod(x, dn);                              // numpy's % on floats (npy_divmod)
+            if (r != 0.0) {
+                if (r < 0.0) r = __dadd_rn(r, dn);
+            } else {
+                r = 0.0;
+            }
+            x = r;
+        }
+        c[p] = x;
+    }
+    if (tid == 0) all_close = 1;
+    __syncthreads();
+    for (int k = 2; k <= np2; k <<= 1)                           // bitonic sort, ascending
+        for (int s = k >> 1; s > 0; s >>= 1) {
+            for (int i = tid; i < np2; i += kThreads) {
+                const int q = i ^ s;
+                if (q > i) {
+                    const double a = c[i], b = c[q];
+                    const bool up = (i & k) == 0;
+                    if ((a > b) == up) {
+                        c[i] = b;
+                        c[q] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    // first argmax of the gaps, and whether all of them are 1 within numpy.isclose (rtol 1e-5, atol 1e-8)
+    double best = -1.0;
+    int best_i = 0x7fffffff;
+    bool close = true;
+    for (int i = tid; i < P - 1; i += kThreads) {
+        const double g = fabs(__dadd_rn(c[i + 1], -c[i]));
+        if (g > best) {
+            best = g;
+            best_i = i;
+        }
+        if (!(fabs(__dadd_rn(g, -1.0)) <= 1e-8 + 1e-5)) close = false;
+    }
+    if (!close) all_close = 0;
+    red_v[tid] = best;
+    red_i[tid] = best_i;
+    __syncthreads();
+    for (int s = kThreads / 2; s > 0; s >>= 1) {
+        if (tid < s) {
+            const double v = red_v[tid + s];
+            const int i = red_i[tid + s];
+            if (v > red_v[tid] || (v == red_v[tid] && i < red_i[tid])) {
+                red_v[tid] = v;
+                red_i[tid] = i;
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) roll_s = (P < 2 || all_close) ? 0 : red_i[0];
+    __syncthreads();
+    const int roll = roll_s;
+    int* oi = axis == 0 ? xi : yi;
+    float* of = axis == 0 ? xf : yf;
+    const size_t o = ((size_t)l * n_steps + step) * P;
+    for (int p = tid; p < P; p += kThreads) {
+        double at = c[(p + roll) % P];
+        at = fmin(at, dn - 1.0);
+        int i0 = (int)floor(at);
+        if (i0 > n - 2) i0 = n - 2;
+        oi[o + p] = i0;
+        of[o + p] = (float)__dadd_rn(at, -(double)i0);
+    }
+}
+
+}  // namespace
+}  // namespace fastb
+
+extern "C" int fastb_temporal_coords(int32_t n, int32_t n_pup, int32_t lo, int32_t n_layers, int32_t steps_per_chunk,
+                                     int32_t n_chunks, const double* d_pixel_shifts, int32_t* d_xi, float* d_xf,
+                                     int32_t* d_yi, float* d_yf, void* stream) {
+    FASTB_REQUIRE(n >= 2 && n_pup >= 1 && n_pup <= n && lo >= 0 && lo + n_pup <= n, "fastb_temporal_coords: bad n / n_pup / lo");
+    FASTB_REQUIRE(n_layers >= 1 && n_layers <= FASTB_MAX_LAYERS, "fastb_temporal_coords: bad n_layers");
+    FASTB_REQUIRE(steps_per_chunk >= 1 && n_chunks >= 0, "fastb_temporal_coords: bad step counts");
+    FASTB_REQUIRE(d_pixel_shifts && d_xi && d_xf && d_yi && d_yf, "fastb_temporal_coords: NULL pointer");
+    const long long rows = 2LL * n_layers * steps_per_chunk * n_chunks;
+    if (rows == 0) return FASTB_OK;
+    FASTB_REQUIRE(rows < (1LL << 31), "fastb_temporal_coords: too many rows");
+    int np2 = 1;
+    while (np2 < n_pup) np2 <<= 1;
+    const size_t smem = sizeof(double) * (size_t)np2;
+    FASTB_CUDA(cudaFuncSetAttribute(temporal_coords_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    temporal_coords_kernel<<<(unsigned)rows, kThreads, smem, (cudaStream_t)stream>>>(
+        n, n_pup, lo, n_layers, steps_per_chunk, n_chunks, d_pixel_shifts, d_xi, d_xf, d_yi, d_yf);
+    return check_launch("temporal_coords_kernel");
+}
+
 extern "C" int fastb_temporal_detect(const FastbTemporalParams* p, const float* d_screens, const int32_t* d_xi,
                                      const float* d_xf, const int32_t* d_yi, const float* d_yf,
                                      const float* d_U, const float* d_chi, float* d_out, void* stream) {

@@ -498,6 +498,7 @@ class Fast():
             # per-step wind shifts in pixels (fast/fast.py:543-544) and the temporal log-amp PSD
             dts = numpy.arange(1, self.Niter_per_chunk + 1) * self.dt
             self.pixel_shifts = dts * self.wind_vector[..., numpy.newaxis] / self.dx
+            d['pixel_shifts'] = torch.from_numpy(numpy.ascontiguousarray(self.pixel_shifts, dtype=numpy.float64)).to(dev)
             ft = self.freq.temporal
             self.temporal_logamp_powerspec = temporal.temporal_logamp_powerspec(
                 self, ft.fx_axis, ft.fy_axis, ft.fabs, self.pupil_filter_temporal)
@@ -706,43 +707,43 @@ class Fast():
                 self.phs = torch.cat([s[0::2], s[1::2]]).cpu().numpy().astype(float)
         return self.phs
 
+    def _temporal_layer_screens(self):
+        """The chunk-0 branch of fast/fast.py:609-616: one real screen per layer on the device
+        (fastb_layer_screens) and the sample coordinates of the first step."""
+        noise = None
+        if self.rng_mode == 'numpy':
+            shape = (len(self.h), self.Npxls, self.Npxls)
+            noise = torch.from_numpy(funcs.generate_random_coefficients(shape).astype(numpy.complex64)).to(self.device)
+        self._d['layer_screens'] = _lib.layer_screens(self._d['weight_per_layer'], self._run_seed(), noise=noise)
+        self.interp_coords = self.pup_coords[numpy.newaxis, :, numpy.newaxis, :].astype(float) \
+            + self.pixel_shifts[:, :, :, numpy.newaxis]
+
     def compute_phs_temporal(self, chunk=0):
-        """TEMPORAL mode (fast/fast.py:607-637).  Chunk 0: one real screen per layer on the
-        device (fastb_layer_screens).  Every chunk: the wind-shifted sample coordinates of its
-        J steps (host, tiny) staged on the device; the gather itself is fused with the detector."""
+        """TEMPORAL mode (fast/fast.py:607-637), one chunk at a time as the reference's loop does.  Chunk 0: the
+        layer screens.  Every chunk: the wind-shifted sample coordinates of its J steps (host numpy, the literal
+        restatement in fast_b200/temporal.py) staged on the device; the gather itself is fused with the detector.
+        Fast.run() does all chunks at once (_run_temporal)."""
         if chunk == 0:
-            noise = None
-            if self.rng_mode == 'numpy':
-                shape = (len(self.h), self.Npxls, self.Npxls)
-                noise = torch.from_numpy(funcs.generate_random_coefficients(shape).astype(numpy.complex64)).to(self.device)
-            self._d['layer_screens'] = _lib.layer_screens(self._d['weight_per_layer'], self._run_seed(), noise=noise)
-            self.interp_coords = self.pup_coords[numpy.newaxis, :, numpy.newaxis, :].astype(float) \
-                + self.pixel_shifts[:, :, :, numpy.newaxis]
+            self._temporal_layer_screens()
         coords = self._advance_temporal_coords()
-        self._d['tcoords_host'] = coords
         self._d['tcoords'] = tuple(torch.from_numpy(c).to(self.device) for c in coords)
         return None
 
     def _run_temporal(self):
-        """Every chunk of a TEMPORAL run in ONE detector launch: the per-chunk sample coordinates (the same host
-        arithmetic, chunk after chunk, as compute_phs_temporal: fast/fast.py:617-635) are stacked along the step
-        axis and staged once, instead of Nchunks rounds of bookkeeping + copies + launches (the run is
-        latency-bound at the reference's sizes).  Leaves the object in the state the chunk loop would."""
-        self.compute_phs_temporal(chunk=0)                  # layer screens + the coordinates of chunk 0
-        # interp_coords chunk after chunk (the same accumulation as the chunk loop), then ONE pass of the coordinate
-        # bookkeeping over the stacked array: the numpy calls are overhead-bound at (L, 2, J, Npup)
+        """Every chunk of a TEMPORAL run in TWO launches after the layer screens: fastb_temporal_coords does the
+        coordinate bookkeeping of all Nchunks x J steps on the device (the reference's arithmetic operation for
+        operation in float64: chunk-after-chunk accumulation, wrap, sort, roll, clamp -- fast/fast.py:617-635) and
+        fastb_temporal_detect gathers and detects them, instead of Nchunks rounds of host bookkeeping + copies +
+        launches (the run is latency-bound at the reference's sizes).  Leaves the object in the state the chunk
+        loop would."""
+        self._temporal_layer_screens()
+        coords = _lib.temporal_coords(self.Npxls, self.Npxls_pup, self._lo, self._d['pixel_shifts'], self.Nchunks)
         step = self.pixel_shifts[:, :, -1, numpy.newaxis, numpy.newaxis]
-        first = self.interp_coords - step                   # what chunk 0 sampled (compute_phs_temporal moved on)
-        stack = [first]
-        for _ in range(1, self.Nchunks):
-            stack.append(stack[-1] + step)
-        self.interp_coords = stack[-1] + step
-        coords = temporal.sample_coordinates(numpy.stack(stack), self.Npxls)       # each (Nchunks, L, J, Npup)
-        L = coords[0].shape[1]
-        staged = tuple(torch.from_numpy(numpy.ascontiguousarray(c.transpose(1, 0, 2, 3)).reshape(L, self.Niter, -1))
-                       .to(self.device) for c in coords)
-        self._d['tcoords'] = tuple(torch.from_numpy(numpy.ascontiguousarray(c[-1])).to(self.device) for c in coords)
-        return self._temporal_detector(0, steps=self.Niter, coords=staged)
+        for _ in range(self.Nchunks):                       # fast/fast.py:635, once per chunk
+            self.interp_coords = self.interp_coords + step
+        J = self.Niter_per_chunk
+        self._d['tcoords'] = tuple(c[:, -J:].contiguous() for c in coords)
+        return self._temporal_detector(0, steps=self.Niter, coords=coords)
 
     def _advance_temporal_coords(self):
         """Sample coordinates of the next chunk from self.interp_coords, which is then moved on by the

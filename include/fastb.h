@@ -332,9 +332,20 @@ int fastb_rng_dump_stride(uint64_t seed, int64_t pair, int32_t n, int32_t stride
  * Fast.compute_detector (fast/fast.py:647-668).  For step j and pupil pixel (a, b)
  *   phi = sum_l bilinear(screen_l; row = xi[l,j,a] + xf[l,j,a], col = yi[l,j,b] + yf[l,j,b])
  *   z_j = exp(chi_j) sum(U exp(i phi)) / sum(U);  out_j = |z_j|^2 or z_j (coherent)
- * The (integer, fraction) sample coordinates, layout [L][n_steps][n_pup], are prepared by the
- * host exactly as the reference does (wrap, sort, roll, FITPACK clamp at N-1), with
- * 0 <= xi, yi <= N-2 and 0 <= xf, yf <= 1.
+ * The (integer, fraction) sample coordinates, layout [L][n_steps][n_pup], follow the reference
+ * exactly (wrap, sort, roll, FITPACK clamp at N-1), with 0 <= xi, yi <= N-2 and 0 <= xf, yf <= 1;
+ * the host may prepare them (fast_b200/temporal.py) or
+ *
+ * K4c fastb_temporal_coords: the coordinate bookkeeping of fast/fast.py:617-635 for EVERY step of a run
+ * (n_chunks chunks of steps_per_chunk steps) on the device, operation for operation in float64 so that
+ * the (integer, fraction) pairs equal numpy's: for layer l, axis (0: rows -> xi / xf, 1: columns ->
+ * yi / yf), chunk c, step j, pupil pixel p
+ *   x = (lo + p) + pixel_shifts[l][axis][j], then + pixel_shifts[l][axis][steps_per_chunk - 1] c times
+ *       (the reference's `interp_coords +=` after every chunk, fast/fast.py:635);
+ *   x mod N (numpy's float modulo), the n_pup values sorted, rolled back by the first argmax of the
+ *   gaps (0 when all gaps are 1 within numpy.isclose), clamped at N - 1, split into floor and fraction.
+ *   d_pixel_shifts  L*2*steps_per_chunk float64 (fast/fast.py:543-544)
+ *   outputs         [L][n_chunks * steps_per_chunk][n_pup]
  * ------------------------------------------------------------------------------------- */
 #define FASTB_LAYER_PAIR_BASE (1ULL << 62)
 
@@ -351,6 +362,10 @@ typedef struct FastbTemporalParams {
     int64_t n_steps;                /* time steps in this call (one chunk) */
     double u_sum;                   /* sum(U) */
 } FastbTemporalParams;
+
+int fastb_temporal_coords(int32_t n, int32_t n_pup, int32_t lo, int32_t n_layers, int32_t steps_per_chunk,
+                          int32_t n_chunks, const double* d_pixel_shifts, int32_t* d_xi, float* d_xf,
+                          int32_t* d_yi, float* d_yf, void* stream);
 
 int fastb_temporal_detect(const FastbTemporalParams* p, const float* d_screens, const int32_t* d_xi,
                           const float* d_xf, const int32_t* d_yi, const float* d_yf, const float* d_U,

@@ -687,3 +687,27 @@ def test_chirp_z_grid_in_every_run_mode(fast):
         np.testing.assert_array_equal(r2, solo.run()._r)
         assert not np.array_equal(r._r, r2)
         assert s_.stats['n'] == 96 and s_.stats['mean'] == pytest.approx(r._r.mean(), rel=1e-6)
+
+
+@pytest.mark.parametrize('N,P,L,J,C,scale', [(164, 82, 4, 10, 10, 3.0), (64, 22, 3, 7, 5, 40.0), (64, 22, 2, 4, 3, 400.0),
+                                              (100, 100, 1, 3, 2, 7.5), (32, 5, 2, 6, 4, 0.0), (512, 300, 2, 2, 3, -90.0)])
+def test_device_coordinate_bookkeeping_equals_the_host_statement(fast, N, P, L, J, C, scale):
+    """K4c fastb_temporal_coords against fast_b200.temporal.sample_coordinates (itself pinned to the literal numpy
+    statement of fast/fast.py:617-635 in tests/test_host_mirror.py): no wrap, partial wraps, many wraps, negative
+    drift, a crop as wide as the grid -- integer parts and float32 fractions bit for bit, chunk after chunk."""
+    from fast_b200 import temporal
+    rng = np.random.default_rng(N + P + J)
+    lo = (N - P) // 2
+    shifts = np.cumsum(rng.random((L, 2, J)), axis=-1) * scale / J
+    got = fast._lib.temporal_coords(N, P, lo, torch.from_numpy(shifts).cuda(), C)
+    pup = np.stack([np.arange(lo, lo + P), np.arange(lo, lo + P)]).astype(int)
+    ic = pup[None, :, None, :].astype(float) + shifts[:, :, :, None]
+    want = []
+    for c in range(C):
+        want.append(temporal.sample_coordinates(ic, N))
+        ic = ic + shifts[:, :, -1, None, None]
+    for k in range(4):
+        w = np.concatenate([x[k] for x in want], axis=1)
+        g = got[k].cpu().numpy()
+        assert g.shape == (L, C * J, P) and g.dtype == w.dtype
+        np.testing.assert_array_equal(g, w)
