@@ -442,14 +442,16 @@ def per_workload(world, rank, flush, peak, dev):
             sim.run()
         dt = (time.perf_counter() - t0) / reps
         out['c1_temporal'] = {"value": sim.Niter / dt, "unit": "time steps/s", "n_gpus": 1, "N": sim.Npxls,
-                              "run_ms": 1e3 * dt, "kernel": "screens_rows/cols_kernel + temporal_detect_kernel",
-                              "note": "test/test_params.py verbatim: wall time of Fast.run() (layer screens + 10 chunks "
-                                      "of 10 steps + host coordinate bookkeeping), latency-bound at this size"}
+                              "run_ms": 1e3 * dt,
+                              "kernel": "layer_lines_kernel (chirp-z) + temporal_coords_kernel + temporal_detect_kernel",
+                              "note": "test/test_params.py verbatim: wall time of Fast.run() -> host result (chi colouring on "
+                                      "the host, layer screens, coordinate bookkeeping of all 10 chunks x 10 steps on the "
+                                      "device, one detector launch, D2H), launch-latency-bound at this size"}
         # C1': same grid, TEMPORAL off -> the chirp-z kernel (N = 164 is not a power of two)
         n_real = 200000
         sim = fast_b200.Fast(configs.c1prime(niter=n_real, nchunks=1, seed=1))
         ms = timed_launches(sim, n_real, 3, flush)
-        entry('c1prime', n_real, ms, sim.Npxls, False, 'screen_detect_bluestein<M=256>')
+        entry('c1prime', n_real, ms, sim.Npxls, False, 'screen_detect_bluestein<M=256, cell class 6>')
         # the O(N^2)-per-line direct kernel on the same grid, for scale
         from fast_b200 import _lib
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
