@@ -669,8 +669,8 @@ class Fast():
 
     def compute_logamp(self):
         """RNG='numpy': host draws in the reference's order (fast/fast.py:639-645);
-        RNG='device': chi is generated inside the kernel and this only clears the buffer."""
-        self.logamp[:] = 0
+        RNG='device': chi is generated inside the kernel; `logamp` keeps the zeros it was created with (no pass over
+        NITER host values per run: 1 ms at 1.2e6 realisations, 7 ms for the 9.6e6 of an 8-GPU step)."""
         if self.temporal:
             # temporally coloured chi: Niter complex draws + one 1-D FFT on the host
             # (fast/funcs.py:367-375).  RNG='device' uses a generator derived from the seed.
@@ -785,6 +785,7 @@ class Fast():
         Successive calls give fresh realisations (see _run_seed)."""
         self._run_index = self._runs
         self._runs += 1
+        self._d.pop('run_stats', None)
         logger.debug("Compute log amplitude values")
         self.compute_logamp()
         ppc = self.Niter_per_chunk // 2
@@ -794,7 +795,15 @@ class Fast():
         elif self.rng_mode != 'numpy':
             rank, world = dist.rank_world()
             lo, hi = dist.shard_range(total, rank, world)
-            a, b = self.screen_detect(lo, hi - lo)
+            # moments / extrema / dB histogram of the run accumulated in the kernel epilogue and combined over the
+            # ranks with one small collective: result_stats() reads them without another pass over the results
+            sb = self._d.get('stats_buffers')
+            if sb is None:
+                sb = self._d['stats_buffers'] = dist.StatsBuffers(4096, self.device)
+            sb.reset()
+            a, b = self.screen_detect(lo, hi - lo, stats=sb)
+            sb.allreduce()
+            self._d['run_stats'] = sb
             a, b = dist.gather_pairs(a, b, total, world)
             flat = dist.assemble(a, b, self.Nchunks, ppc)
         else:
@@ -838,6 +847,9 @@ class Fast():
     def result_stats(self, db_lo=-60.0, db_hi=3.0, nbins=4096):
         """Moments / extrema / dB histogram of the last run computed on the device
         (fastb_stats) and, under torch.distributed, all-reduced over the ranks' shards."""
+        sb = self._d.get('run_stats')
+        if sb is not None and (sb.db_lo, sb.db_hi, sb.nbins) == (float(db_lo), float(db_hi), int(nbins)):
+            return sb.summary()                    # fused into the run's kernel epilogue, already global
         r = self._d['result']
         if r.is_complex():
             r = (r.real ** 2 + r.imag ** 2).contiguous()

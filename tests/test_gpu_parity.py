@@ -711,3 +711,24 @@ def test_device_coordinate_bookkeeping_equals_the_host_statement(fast, N, P, L, 
         g = got[k].cpu().numpy()
         assert g.shape == (L, C * J, P) and g.dtype == w.dtype
         np.testing.assert_array_equal(g, w)
+
+
+def test_run_leaves_the_fused_statistics_of_the_run(fast):
+    """Fast.run() accumulates moments / extrema / dB histogram in the kernel epilogue: result_stats() with the default
+    binning returns them (equal to a pass of fastb_stats over the results), other binnings recompute."""
+    g, p = load_golden('c2')
+    sim = fast.Fast(dict(p, NITER=20000, NCHUNKS=4, SEED=12))
+    res = sim.run()
+    fused = sim.result_stats()
+    assert fused['n'] == 20000
+    assert fused['mean'] == pytest.approx(res._r.mean(), rel=1e-6)
+    assert fused['mean_dB'] == pytest.approx(res.dB_rel.mean(), rel=1e-6)
+    assert fused['min'] == pytest.approx(res._r.min(), rel=1e-6) and fused['max'] == pytest.approx(res._r.max(), rel=1e-6)
+    other = sim.result_stats(db_lo=-40, db_hi=5, nbins=450)
+    assert other['n'] == 20000 and other['mean'] == pytest.approx(fused['mean'], rel=1e-9)
+    h, _ = np.histogram(res.dB_rel, bins=450, range=(-40, 5))
+    assert np.abs(other['hist'][:450] - h).sum() <= 4
+    # a second run replaces them
+    res2 = sim.run()
+    assert sim.result_stats()['mean'] == pytest.approx(res2._r.mean(), rel=1e-6)
+    assert sim.result_stats()['mean'] != fused['mean']
